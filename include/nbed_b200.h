@@ -1,0 +1,142 @@
+/* nbed_b200 — C-ABI of the B200-native Nbed hot path (sm_100a).
+ *
+ * Drop-in boundary.  The reference (UCL-CCS/Nbed) is pure Python on top of PySCF; the
+ * arithmetic of its hot path is reached through PySCF's ctypes bindings.  Every entry point below states
+ * the reference interface it replaces (paths relative to the reference tree).  Conventions mirror
+ * PySCF's own ctypes style: C-contiguous float64 host arrays passed as plain pointers, sizes by value,
+ * caller allocates outputs, calls block until the result is in the caller's buffer, no exceptions cross
+ * the ABI: every function returns 0 on success or a negative nbd_status, and nbd_last_error() gives text.
+ *
+ * One context per process and per GPU (one process per GPU; multi-GPU = aux-index shards + NCCL
+ * all-reduce, see nbd_comm_init).  A context is not re-entrant.
+ */
+#ifndef NBED_B200_H
+#define NBED_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nbd_ctx nbd_ctx;
+
+enum nbd_status {
+  NBD_OK = 0,
+  NBD_ERR_CUDA = -1,       /* a CUDA / cuSOLVER / NCCL call failed                         */
+  NBD_ERR_ARG = -2,        /* bad argument (shape, null pointer, state)                      */
+  NBD_ERR_STATE = -3,      /* call order violated (e.g. J/K before the 3-centre tensor)      */
+  NBD_ERR_UNSUPPORTED = -4 /* outside the implemented envelope (e.g. nao > 3072)             */
+};
+
+enum nbd_projector { NBD_HUZINAGA = 0, NBD_MU_SHIFT = 1 };
+
+/* ---- context ------------------------------------------------------------------------------- */
+int nbd_version(void);
+int nbd_create(nbd_ctx** out, int device);
+int nbd_destroy(nbd_ctx* ctx);
+const char* nbd_last_error(nbd_ctx* ctx);
+/* Tuning / debugging knobs ("jk_variant": 0 = DMMA pipeline, 1 = simple reference kernels;
+ * "gemm_variant": 0 = DMMA tiles, 1 = simple).  Returns NBD_ERR_ARG for an unknown key. */
+int nbd_set_option(nbd_ctx* ctx, const char* key, long value);
+/* Per-stage device timings (CUDA events) of the last call, in milliseconds.
+ * keys: "jk_x", "jk_rho", "jk_j", "jk_k", "jk_total", "allreduce", "fock", "diis", "orth", "eigh",
+ *       "density", "energy", "ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_total", "iter_total".   */
+double nbd_timer_ms(nbd_ctx* ctx, const char* key);
+/* Number of kernels launched by this library since the context was created (bench "gpu_launches"). */
+long nbd_launch_count(nbd_ctx* ctx);
+
+/* ---- multi-GPU plumbing -------------------------------------------------------------------- */
+/* NCCL communicator over the ranks that share one 3-centre tensor by auxiliary index.
+ * unique_id: the 128 bytes of ncclUniqueId made by rank 0 (nbd_comm_unique_id) and broadcast by the host
+ * layer (torch.distributed).  After this call J/K and ao2mo results are all-reduced across ranks. */
+int nbd_comm_unique_id(void* unique_id_128);
+int nbd_comm_init(nbd_ctx* ctx, const void* unique_id_128, int rank, int world);
+
+/* ---- 3-centre tensor (P|mu nu): uploaded once per geometry, NOT in the timed loop ----------- */
+/* Replaces: pyscf `mf.with_df._cderi` (what `mf.density_fit()` builds through libcint; reference J/K call
+ * sites nbed/scf/huzinaga_scf.py:156, nbed/scf/embedded_hcore_funcs.py:34, nbed/driver.py:533).
+ * naux_local rows of this rank's shard are stored in the tiled-triangular device layout. */
+int nbd_cderi_alloc(nbd_ctx* ctx, int nao, int naux_local);
+/* rows [row0, row0+nrows) of the LOCAL shard, host layout = PySCF packed-lower [nrows, nao(nao+1)/2]. */
+int nbd_cderi_upload(nbd_ctx* ctx, const double* cderi_rows, int row0, int nrows);
+/* Synthetic tensor filled on the device (bench / large-size tests): value of global row
+ * (global_row0 + local row) as defined by nbed_b200/synthetic.py:hash_uniform. */
+int nbd_cderi_synth(nbd_ctx* ctx, unsigned long long seed, double scale, int global_row0);
+/* Read back local rows in packed-lower layout (round-trip test of the layout transform). */
+int nbd_cderi_download(nbd_ctx* ctx, double* cderi_rows, int row0, int nrows);
+
+/* ---- J/K --------------------------------------------------------------------------------------- */
+/* Replaces: pyscf.df.df_jk.get_jk occupied-orbital branch (reached from scf_method.get_veff / get_jk /
+ * get_j: nbed/scf/huzinaga_scf.py:55,156; nbed/scf/embedded_hcore_funcs.py:34; nbed/driver.py:344-345,
+ * 391,533,627,847,849).
+ * orb: host [nset][nao][ncol[s]] concatenated per set, C-contiguous: scaled occupied orbitals
+ *      C_occ*sqrt(occ) (or signed eigen-factors of a dense density, sign[] = +1/-1 per column, may be NULL).
+ * vj : host [nset][nao][nao] (NULL to skip J)   vk: host [nset][nao][nao] (NULL to skip K).
+ * Results are summed over all ranks of the communicator. */
+int nbd_jk(nbd_ctx* ctx, int nset, const int* ncol, const double* orb, const double* sign,
+           double* vj, double* vk);
+/* Dense-density entry (pyscf get_jk without mo_coeff tags): dm host [nset][nao][nao], symmetric. */
+int nbd_jk_dm(nbd_ctx* ctx, int nset, const double* dm, double* vj, double* vk);
+
+/* ---- embedded SCF ------------------------------------------------------------------------------ */
+/* Static matrices of one embedded SCF problem.
+ * Replaces the set-up of nbed/scf/huzinaga_scf.py:126-136 (S, S^-1/2, gamma*S) and of
+ * nbed/driver.py:433-449,518 (mu * S gamma S + V folded into the core Hamiltonian).
+ * ovlp [nao][nao]; hcore [nao][nao]; v_emb [nspin][nao][nao]; dm_env [nspin][nao][nao] (nspin = 1: RHF
+ * rank-2 convention with the doubled density and the -1/2 factor of huzinaga_scf.py:80). */
+int nbd_scf_setup(nbd_ctx* ctx, int nspin, const int* nelec, const double* ovlp, const double* hcore,
+                  const double* v_emb, const double* dm_env, int projector, double mu);
+
+typedef struct nbd_scf_result {
+  int converged;      /* conv flag                                              */
+  int cycles;         /* number of Fock builds executed in the loop             */
+  double e_tot;       /* mu path: PySCF e_tot (incl. e_nuc passed in); Huzinaga: sum of last scf_energy */
+  double energy[2];   /* Huzinaga: per-spin scf_energy of the last cycle (huzinaga_scf.py:185) */
+  double norm_ddm;    /* last density change                                    */
+  double norm_grad;   /* mu path: last orbital-gradient norm                    */
+} nbd_scf_result;
+
+/* Replaces: nbed.scf.huzinaga_scf (nbed/scf/huzinaga_scf.py:93-206), HF objects.
+ * dm0: optional initial guess [nspin][nao][nao] (NULL = core guess of :139-148).
+ * Outputs (caller-allocated, may be NULL): mo_coeff [nspin][nao][nao] (columns = MOs),
+ * mo_energy [nspin][nao], dm [nspin][nao][nao], huz [nspin][nao][nao] (pre-DIIS operator of the last
+ * cycle), trace [max_cycle][3] = per-cycle (E_alpha, E_beta, max ||dD||_F). */
+int nbd_huzinaga_scf(nbd_ctx* ctx, int max_cycle, double conv_tol, double dm_conv_tol, int use_diis,
+                     const double* dm0, double* mo_coeff, double* mo_energy, double* dm, double* huz,
+                     double* trace, nbd_scf_result* result);
+
+/* Replaces: pyscf.scf.hf.kernel as driven by NbedDriver._mu_embed (nbed/driver.py:500-538) with the
+ * patched get_hcore (:529) and energy_elec (nbed/scf/embedded_hcore_funcs.py:11-46); CDIIS error vector
+ * F D S - S D F; generalised eigensolve = cuSOLVER dsygvd.  dm0 [nspin][nao][nao] is required.
+ * trace [max_cycle+1][3] = per-cycle (e_tot, ||g||, ||dD||). */
+int nbd_mu_scf(nbd_ctx* ctx, int max_cycle, double conv_tol, double e_nuc, const double* dm0,
+               double* mo_coeff, double* mo_energy, double* mo_occ, double* dm, double* vhf,
+               double* trace, nbd_scf_result* result);
+
+/* One Fock-build iteration on device-resident state, for benchmarks (K1-K6 of SURVEY.md §2.3):
+ * J/K from the current occupied orbitals, Fock + projector, DIIS push/extrapolate, orthogonalise,
+ * eigensolve, back-transform, density, energy and convergence scalars.  Requires nbd_scf_setup and a
+ * prior nbd_scf_bench_init (core guess).  with_eigh = 0 skips nothing: the eigensolve is always executed;
+ * its time is reported separately under the "eigh" timer key. */
+int nbd_scf_bench_init(nbd_ctx* ctx);
+int nbd_scf_bench_iteration(nbd_ctx* ctx, int iter, double* energy2, double* norm_ddm);
+
+/* ---- active-space AO->MO transform --------------------------------------------------------------- */
+/* Replaces: HamiltonianBuilder._two_body_integrals (nbed/ham_builder.py:98-156): the four
+ * pyscf.ao2mo.kernel + ao2mo.restore(1) + transpose(0,2,3,1) blocks.
+ * ca, cb: host [nao][m] (pass cb = ca or NULL for the restricted case).
+ * out: host [4][m][m][m][m], out[blk][p][r][s][q] = (p q | r s), blk = aaaa, bbbb, aabb, bbaa. */
+int nbd_ao2mo(nbd_ctx* ctx, int m, const double* ca, const double* cb, double* out);
+/* Replaces: HamiltonianBuilder._one_body_integrals (nbed/ham_builder.py:53-96): C^T h C per spin.
+ * hcore [nspin_h][nao][nao] (nspin_h = 1 or 2), out [2][m][m]. */
+int nbd_one_body(nbd_ctx* ctx, int m, int nspin_h, const double* hcore, const double* ca, const double* cb,
+                 double* out);
+/* Replaces: HamiltonianBuilder._spinorb_from_spatial + the 0.5 factor of build()
+ * (nbed/ham_builder.py:158-216,254).  one [2][m][m], two [4][m][m][m][m] (host);
+ * h1 [2m][2m], h2 [2m][2m][2m][2m] (host); |x| < eq_tol -> 0; h2 is scaled by two_body_scale (0.5). */
+int nbd_spinorb_from_spatial(nbd_ctx* ctx, int m, const double* one, const double* two, double eq_tol,
+                             double two_body_scale, double* h1, double* h2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBED_B200_H */

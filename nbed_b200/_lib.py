@@ -1,0 +1,100 @@
+"""ctypes binding of the C-ABI library (include/nbed_b200.h).  No CPU fallback: if the CUDA library is
+missing or a call fails, this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnbed_b200.so")
+
+NBD_HUZINAGA = 0
+NBD_MU_SHIFT = 1
+
+# every symbol include/nbed_b200.h declares (tests check that the built library exports all of them)
+EXPORTS = [
+    "nbd_version", "nbd_create", "nbd_destroy", "nbd_last_error", "nbd_set_option", "nbd_timer_ms",
+    "nbd_launch_count", "nbd_comm_unique_id", "nbd_comm_init", "nbd_cderi_alloc", "nbd_cderi_upload",
+    "nbd_cderi_synth", "nbd_cderi_download", "nbd_jk", "nbd_jk_dm", "nbd_scf_setup", "nbd_huzinaga_scf",
+    "nbd_mu_scf", "nbd_scf_bench_init", "nbd_scf_bench_iteration", "nbd_ao2mo", "nbd_one_body",
+    "nbd_spinorb_from_spatial",
+]
+
+
+class NbdError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"nbed_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ScfResult(C.Structure):
+    _fields_ = [
+        ("converged", C.c_int),
+        ("cycles", C.c_int),
+        ("e_tot", C.c_double),
+        ("energy", C.c_double * 2),
+        ("norm_ddm", C.c_double),
+        ("norm_grad", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load (once) the in-tree CUDA library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m nbed_b200.build` (nvcc, sm_100a). "
+            "nbed_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    P, I, D, L = C.c_void_p, C.c_int, C.c_double, C.c_long
+    sig = {
+        "nbd_version": (I, []),
+        "nbd_create": (I, [C.POINTER(P), I]),
+        "nbd_destroy": (I, [P]),
+        "nbd_last_error": (C.c_char_p, [P]),
+        "nbd_set_option": (I, [P, C.c_char_p, L]),
+        "nbd_timer_ms": (D, [P, C.c_char_p]),
+        "nbd_launch_count": (L, [P]),
+        "nbd_comm_unique_id": (I, [P]),
+        "nbd_comm_init": (I, [P, P, I, I]),
+        "nbd_cderi_alloc": (I, [P, I, I]),
+        "nbd_cderi_upload": (I, [P, P, I, I]),
+        "nbd_cderi_synth": (I, [P, C.c_ulonglong, D, I]),
+        "nbd_cderi_download": (I, [P, P, I, I]),
+        "nbd_jk": (I, [P, I, P, P, P, P, P]),
+        "nbd_jk_dm": (I, [P, I, P, P, P]),
+        "nbd_scf_setup": (I, [P, I, P, P, P, P, P, I, D]),
+        "nbd_huzinaga_scf": (I, [P, I, D, D, I, P, P, P, P, P, P, C.POINTER(ScfResult)]),
+        "nbd_mu_scf": (I, [P, I, D, D, P, P, P, P, P, P, P, C.POINTER(ScfResult)]),
+        "nbd_scf_bench_init": (I, [P]),
+        "nbd_scf_bench_iteration": (I, [P, I, P, P]),
+        "nbd_ao2mo": (I, [P, I, P, P, P]),
+        "nbd_one_body": (I, [P, I, I, P, P, P, P]),
+        "nbd_spinorb_from_spatial": (I, [P, I, P, P, D, D, P, P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(a):
+    """Pointer to a C-contiguous float64 / int32 array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)

@@ -1,0 +1,383 @@
+// Density-fitted Coulomb / exchange build over the device-resident 3-centre tensor.
+//
+//   pass 1  X[P][i][mu] = sum_nu B[P][mu][nu] Ct[i][nu]        (symm_panel_kernel: B streamed ONCE, FP64 DMMA)
+//           rho[P]      = sum_{i,mu} w_i Ct[i][mu] X[P][i][mu]  (rho_kernel; = sum_{mu nu} B D, D = sum_i w_i c_i c_i^T)
+//   pass 2  J           = sum_P rho[P] B[P]                     (j_pass_kernel: second compulsory pass, HBM bound)
+//           K_s         = sum_{P, i in s} w_i X[P][i] X[P][i]^T (gemm.cuh, lower tiles, K-dim = naux*nocc)
+//
+// The reference reaches the same contraction through pyscf.df.df_jk.get_jk (occupied-orbital branch) from
+// nbed/scf/huzinaga_scf.py:156 and nbed/scf/embedded_hcore_funcs.py:34.
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace nbd {
+
+// ---------------------------------------------------------------------------------------------------
+// Tile order.  Panels of 32 AOs; tile (I, J), J <= I.  Consumer warp (I % 8) owns the "row" update
+// X[I] += B_IJ C_J and warp (J % 8) the "column" update X[J] += B_IJ^T C_I, so inside every run of 8
+// consecutive tiles of this skewed order all 8 warps get one task of each kind.
+// ---------------------------------------------------------------------------------------------------
+inline std::vector<int> build_tile_sequence(int nb) {
+  std::vector<int> seq;
+  const int nsb = (nb + 7) / 8;
+  for (int a = 0; a < nsb; ++a)
+    for (int b = 0; b <= a; ++b)
+      for (int k = 0; k < 8; ++k)
+        for (int j = 0; j < 8; ++j) {
+          const int I = 8 * a + (j + k) % 8, J = 8 * b + j;
+          if (I >= nb || J >= nb || J > I) continue;
+          seq.push_back((I << 16) | J);
+        }
+  return seq;
+}
+
+__host__ __device__ __forceinline__ long packed_index(int mu, int nu) {
+  const int hi = mu > nu ? mu : nu, lo = mu > nu ? nu : mu;
+  return (long)hi * (hi + 1) / 2 + lo;
+}
+
+// ---- layout transforms -----------------------------------------------------------------------------
+// packed rows (device staging, [nrows][npair]) -> tiled; one CTA per (tile, row)
+__global__ void pack_to_tiled_kernel(const double* __restrict__ packed, double* __restrict__ tiled,
+                                     const int* __restrict__ seq, int ntiles, int n, long npair, int row0) {
+  const int k = blockIdx.x, p = blockIdx.y;
+  const int I = seq[k] >> 16, J = seq[k] & 0xffff;
+  const double* src = packed + (long)p * npair;
+  double* dst = tiled + ((long)(row0 + p) * ntiles + k) * TILE_ELEMS;
+  for (int e = threadIdx.x; e < TILE_ELEMS; e += blockDim.x) {
+    const int r = e >> 5, c = e & 31;
+    const int mu = 32 * I + r, nu = 32 * J + c;
+    double v = 0.0;
+    if (mu < n && nu < n) v = src[packed_index(mu, nu)];
+    dst[tile_swz(r, c)] = v;
+  }
+}
+
+__global__ void tiled_to_packed_kernel(const double* __restrict__ tiled, double* __restrict__ packed,
+                                       const int* __restrict__ seq, int ntiles, int n, long npair, int row0) {
+  const int k = blockIdx.x, p = blockIdx.y;
+  const int I = seq[k] >> 16, J = seq[k] & 0xffff;
+  double* dst = packed + (long)p * npair;
+  const double* src = tiled + ((long)(row0 + p) * ntiles + k) * TILE_ELEMS;
+  for (int e = threadIdx.x; e < TILE_ELEMS; e += blockDim.x) {
+    const int r = e >> 5, c = e & 31;
+    const int mu = 32 * I + r, nu = 32 * J + c;
+    if (mu < n && nu < n && nu <= mu) dst[packed_index(mu, nu)] = src[tile_swz(r, c)];
+  }
+}
+
+// SplitMix64 -> uniform [-1,1): bit-identical to nbed_b200/synthetic.py:hash_uniform
+__device__ __forceinline__ double synth_uniform(unsigned long long seed, unsigned long long index) {
+  unsigned long long z = (seed << 48) + index + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+}
+
+__global__ void synth_tiled_kernel(double* __restrict__ tiled, const int* __restrict__ seq, int ntiles, int n,
+                                   long npair, unsigned long long seed, double scale, int global_row0) {
+  const int k = blockIdx.x, p = blockIdx.y;
+  const int I = seq[k] >> 16, J = seq[k] & 0xffff;
+  double* dst = tiled + ((long)p * ntiles + k) * TILE_ELEMS;
+  for (int e = threadIdx.x; e < TILE_ELEMS; e += blockDim.x) {
+    const int r = e >> 5, c = e & 31;
+    const int mu = 32 * I + r, nu = 32 * J + c;
+    double v = 0.0;
+    if (mu < n && nu < n)
+      v = scale * synth_uniform(seed, (unsigned long long)(global_row0 + p) * (unsigned long long)npair +
+                                          (unsigned long long)packed_index(mu, nu));
+    dst[tile_swz(r, c)] = v;
+  }
+}
+
+// ---- pass 1: X = B_sym * C, one B tile enters the SM once and is used in both directions -------------
+struct XArgs {
+  const double* Bt;   // [naux][ntiles][1024]
+  const int* seq;     // [ntiles]
+  const double* Ct;   // [Ntot][n_ld]
+  double* X;          // [naux][Ntot][n_ld]
+  int naux, ntiles, nb, n_ld, Ntot, nslices, nstages;
+};
+
+// 8 consumer warps (warpgroups 0-1) + one producer warpgroup.  Registers are re-balanced with setmaxnreg
+// (the accumulators of a 1376-AO row set need ~200 registers per consumer thread; a 9-warp CTA would be
+// capped at 168 because the register file is split per SM sub-partition).
+constexpr int XK_CONSUMER_WARPS = 8;
+constexpr int XK_THREADS = (XK_CONSUMER_WARPS + 4) * 32;
+constexpr int XK_CONSUMER_REGS = 240;
+constexpr int XK_PRODUCER_REGS = 24;
+
+template <int NB>
+__device__ __forceinline__ void xk_task_row(double (&acc)[4][NB][2], const double* __restrict__ tile,
+                                            const double* const (&crow)[NB], int colbase, int gq, int tq,
+                                            const int (&xoff)[4]) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    double a[4], b[NB];
+    const int co = ((ks >> 2) << 4) + xoff[ks & 3];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) a[mi] = tile[(8 * mi + gq) * 32 + co];
+#pragma unroll
+    for (int ni = 0; ni < NB; ++ni) b[ni] = crow[ni][colbase + 4 * ks + tq];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NB; ++ni) dmma(acc[mi][ni], a[mi], b[ni]);
+  }
+}
+
+template <int NB>
+__device__ __forceinline__ void xk_task_col(double (&acc)[4][NB][2], const double* __restrict__ tile,
+                                            const double* const (&crow)[NB], int colbase, int tq,
+                                            const int (&yoff)[4]) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    double a[4], b[NB];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) a[mi] = tile[(4 * ks + tq) * 32 + yoff[mi]];
+#pragma unroll
+    for (int ni = 0; ni < NB; ++ni) b[ni] = crow[ni][colbase + 4 * ks + tq];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NB; ++ni) dmma(acc[mi][ni], a[mi], b[ni]);
+  }
+}
+
+// NSLOT = ceil(nb / 8) panels owned per consumer warp; NB = 8-column blocks per slice (1 or 2).
+template <int NSLOT, int NB>
+__global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
+  extern __shared__ __align__(128) unsigned char xsm[];
+  constexpr int NCOL = 8 * NB;
+  const int S = p.nstages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(xsm);
+  uint64_t* empty = full + 16;
+  const int ct_ld = p.n_ld + 4;
+  const int slice = blockIdx.x % p.nslices;
+  const int col0 = slice * NCOL;
+  const int ncol = min(NCOL, p.Ntot - col0);
+  double* cts = reinterpret_cast<double*>(xsm + 256);
+  // stage buffers start at the next 128-byte boundary after (ncol + 1) rows of Ct
+  const size_t ct_bytes = ((size_t)(ncol + 1) * ct_ld * 8 + 127) & ~(size_t)127;
+  double* stages = reinterpret_cast<double*>(xsm + 256 + ct_bytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 2);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const long nitems = (long)p.naux * p.nslices;
+  // items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ... (gridDim.x is a multiple of nslices)
+
+  if (warp >= XK_CONSUMER_WARPS) {
+    // ===== producer warpgroup: one lane streams the tiles of every item of this CTA through the ring =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(XK_PRODUCER_REGS));
+    if (warp == XK_CONSUMER_WARPS && lane == 0) {
+      long q = 0;
+      for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const long P = item / p.nslices;
+        const double* src = p.Bt + P * (long)p.ntiles * TILE_ELEMS;
+        for (int k = 0; k < p.ntiles; ++k, ++q) {
+          const int st = (int)(q % S);
+          if (q >= S) mbar_wait(&empty[st], (uint32_t)((q / S - 1) & 1));
+          mbar_expect_tx(&full[st], TILE_BYTES);
+          bulk_g2s(stages + (size_t)st * TILE_ELEMS, src + (long)k * TILE_ELEMS, TILE_BYTES, &full[st]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(XK_CONSUMER_REGS));
+  for (int i = 0; i <= ncol; ++i) {
+    double* dst = cts + (size_t)i * ct_ld;
+    if (i < ncol) {
+      const double* src = p.Ct + (size_t)(col0 + i) * p.n_ld;
+      for (int m = tid; m < p.n_ld; m += XK_CONSUMER_WARPS * 32) dst[m] = src[m];
+    } else {
+      for (int m = tid; m < p.n_ld; m += XK_CONSUMER_WARPS * 32) dst[m] = 0.0;
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(XK_CONSUMER_WARPS * 32) : "memory");
+
+  const int gq = lane >> 2, tq = lane & 3;
+  int xoff[4], yoff[4];
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) xoff[q4] = 4 * (q4 ^ (gq & 3)) + tq;
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) yoff[mi] = (8 * mi + gq) ^ (4 * tq);
+  const double* crow[NB];
+#pragma unroll
+  for (int ni = 0; ni < NB; ++ni) crow[ni] = cts + (size_t)min(8 * ni + gq, ncol) * ct_ld;
+
+  double X[NSLOT][4][NB][2];
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s)
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NB; ++ni) X[s][mi][ni][0] = X[s][mi][ni][1] = 0.0;
+
+  long q = 0;
+  for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const long P = item / p.nslices;
+    for (int k = 0; k < p.ntiles; ++k, ++q) {
+      const int ij = __ldg(p.seq + k);
+      const int I = ij >> 16, J = ij & 0xffff;
+      const bool do_row = (I & 7) == warp;
+      const bool do_col = ((J & 7) == warp) && (I != J);
+      if (!do_row && !do_col) continue;
+      const int st = (int)(q % S);
+      mbar_wait(&full[st], (uint32_t)((q / S) & 1));
+      const double* tile = stages + (size_t)st * TILE_ELEMS;
+      if (do_row) {
+        const int slot = I >> 3;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+          if (slot == s) xk_task_row<NB>(X[s], tile, crow, 32 * J, gq, tq, xoff);
+      }
+      if (do_col) {
+        const int slot = J >> 3;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+          if (slot == s) xk_task_col<NB>(X[s], tile, crow, 32 * I, tq, yoff);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st], (do_row ? 1u : 0u) + (do_col ? 1u : 0u) + (I == J ? 1u : 0u));
+    }
+    // write this warp's panels of X[P] and reset the accumulators
+    double* xo = p.X + ((size_t)P * p.Ntot + col0) * p.n_ld;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int I = 8 * s + warp;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NB; ++ni)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int i = 8 * ni + 2 * tq + r;
+            if (I < p.nb && i < ncol) xo[(size_t)i * p.n_ld + 32 * I + 8 * mi + gq] = X[s][mi][ni][r];
+            X[s][mi][ni][r] = 0.0;
+          }
+    }
+  }
+}
+
+// Obviously-correct variant (option "jk_variant" = 1): one CTA per (P, panel), CUDA cores.
+__global__ void symm_panel_simple_kernel(const double* __restrict__ Bt, const int* __restrict__ inv,
+                                         const double* __restrict__ Ct, double* __restrict__ X, int ntiles,
+                                         int nb, int n_ld, int Ntot) {
+  const int P = blockIdx.y, I = blockIdx.x;
+  const double* bp = Bt + (long)P * ntiles * TILE_ELEMS;
+  for (int e = threadIdx.x; e < 32 * Ntot; e += blockDim.x) {
+    const int r = e & 31, i = e >> 5;
+    const int mu = 32 * I + r;
+    double s = 0.0;
+    for (int nu = 0; nu < n_ld; ++nu) {
+      const int Jn = nu >> 5, c = nu & 31;
+      double b;
+      if (Jn <= I) b = bp[(long)inv[I * nb + Jn] * TILE_ELEMS + tile_swz(r, c)];
+      else b = bp[(long)inv[Jn * nb + I] * TILE_ELEMS + tile_swz(c, r)];
+      s += b * Ct[(long)i * n_ld + nu];
+    }
+    X[((long)P * Ntot + i) * n_ld + mu] = s;
+  }
+}
+
+// rho[set][P] (+)= sum_{i in set} sum_mu X[P][i][mu] * Wt[i][mu]   (Wt = sign_i * Ct)
+__global__ void rho_kernel(const double* __restrict__ X, const double* __restrict__ Wt, double* __restrict__ rho,
+                           int naux, int n_ld, int Ntot, int nset, const int* __restrict__ set_begin,
+                           int accumulate) {
+  __shared__ double red[32];
+  const int P = blockIdx.x;
+  for (int s = 0; s < nset; ++s) {
+    const int i0 = set_begin[s], i1 = set_begin[s + 1];
+    const double* x = X + ((long)P * Ntot + i0) * n_ld;
+    const double* w = Wt + (long)i0 * n_ld;
+    const long cnt = (long)(i1 - i0) * n_ld;
+    double v = 0.0;
+    for (long e = threadIdx.x; e < cnt; e += blockDim.x) v += x[e] * w[e];
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) {
+      if (accumulate) rho[(long)s * naux + P] += v;
+      else rho[(long)s * naux + P] = v;
+    }
+  }
+}
+
+// ---- pass 2: J (tiled layout) = sum_P rho[P] * B[P]; split over P, partials reduced by j_finalize ----
+template <int NSET>
+__global__ void __launch_bounds__(256) j_pass_kernel(const double2* __restrict__ Bt, const double* __restrict__ rho,
+                                                     double2* __restrict__ part, long E2, int naux,
+                                                     int rows_per_split) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= E2) return;
+  const int split = blockIdx.y;
+  const int p0 = split * rows_per_split;
+  const int p1 = min(naux, p0 + rows_per_split);
+  double2 acc[NSET];
+#pragma unroll
+  for (int s = 0; s < NSET; ++s) acc[s] = make_double2(0.0, 0.0);
+  const double2* b = Bt + idx;
+  int p = p0;
+  for (; p + 8 <= p1; p += 8) {
+    double2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcs(b + (long)(p + u) * E2);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int s = 0; s < NSET; ++s) {
+        const double r = __ldg(rho + (long)s * naux + p + u);
+        acc[s].x = fma(r, v[u].x, acc[s].x);
+        acc[s].y = fma(r, v[u].y, acc[s].y);
+      }
+    }
+  }
+  for (; p < p1; ++p) {
+    const double2 v = __ldcs(b + (long)p * E2);
+#pragma unroll
+    for (int s = 0; s < NSET; ++s) {
+      const double r = __ldg(rho + (long)s * naux + p);
+      acc[s].x = fma(r, v.x, acc[s].x);
+      acc[s].y = fma(r, v.y, acc[s].y);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NSET; ++s) part[((long)split * NSET + s) * E2 + idx] = acc[s];
+}
+
+// J[set][mu][nu] (square, symmetric) from the split partials in tiled layout
+__global__ void j_finalize_kernel(const double* __restrict__ part, const int* __restrict__ inv, double* __restrict__ J,
+                                  int n, int nb, long E, int nsplit, int nset) {
+  const int nu = blockIdx.x * blockDim.x + threadIdx.x;
+  const int mu = blockIdx.y;
+  if (nu >= n) return;
+  const int hi = max(mu, nu), lo = min(mu, nu);
+  const int I = hi >> 5, Jt = lo >> 5;
+  const long off = (long)inv[I * nb + Jt] * TILE_ELEMS + tile_swz(hi & 31, lo & 31);
+  for (int s = 0; s < nset; ++s) {
+    double v = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) v += part[((long)sp * nset + s) * E + off];
+    J[((long)s * n + mu) * n + nu] = v;
+  }
+}
+
+// mirror the lower triangle of `batch` square matrices into the upper triangle
+__global__ void symmetrize_lower_kernel(double* __restrict__ A, int n, long stride) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  double* a = A + (long)blockIdx.z * stride;
+  if (j < n && j > i) a[(long)i * n + j] = a[(long)j * n + i];
+}
+
+}  // namespace nbd

@@ -1,0 +1,825 @@
+// nbed_b200 — C-ABI implementation (see include/nbed_b200.h).  sm_100a only.
+//
+// Everything numerical runs in the hand-written kernels of jk.cuh / gemm.cuh / scf_kernels.cuh; the only
+// library routines on the path are the cuSOLVER eigensolvers the north star names (dsyevd / dsygvd, timed
+// separately under the "eigh" key) and NCCL's all-reduce for the aux-sharded partial J/K and MO integrals.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "host_util.cuh"
+#include "jk.cuh"
+#include "scf_kernels.cuh"
+
+using namespace nbd;
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen) so that the library loads on hosts without it.
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string& why) {
+    if (lib) return true;
+    const char* env = getenv("NBD_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      if (!nm || !*nm) continue;
+      lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) {
+      why = "cannot dlopen libnccl.so.2 (set NBD_NCCL_LIB, or import torch first)";
+      return false;
+    }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString) {
+      why = "libnccl is missing required symbols";
+      return false;
+    }
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
+// ------------------------------------------------------------------------------------------------
+// Small host linear algebra for the DIIS equations (<= 9 x 9): restates what pyscf/lib/diis.py asks of
+// scipy.linalg.eigh / numpy.linalg.solve (reference call site nbed/scf/huzinaga_scf.py:164).
+// ------------------------------------------------------------------------------------------------
+static void jacobi_eigh(int n, std::vector<double> a, std::vector<double>& w, std::vector<double>& v) {
+  v.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) v[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) off += a[(size_t)p * n + q] * a[(size_t)p * n + q];
+    if (off < 1e-300) break;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = a[(size_t)p * n + q];
+        if (apq == 0.0) continue;
+        const double app = a[(size_t)p * n + p], aqq = a[(size_t)q * n + q];
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double akp = a[(size_t)k * n + p], akq = a[(size_t)k * n + q];
+          a[(size_t)k * n + p] = c * akp - s * akq;
+          a[(size_t)k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = a[(size_t)p * n + k], aqk = a[(size_t)q * n + k];
+          a[(size_t)p * n + k] = c * apk - s * aqk;
+          a[(size_t)q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = v[(size_t)k * n + p], vkq = v[(size_t)k * n + q];
+          v[(size_t)k * n + p] = c * vkp - s * vkq;
+          v[(size_t)k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  w.resize(n);
+  for (int i = 0; i < n; ++i) w[i] = a[(size_t)i * n + i];
+}
+
+static bool lu_solve(int n, std::vector<double> a, std::vector<double> b, std::vector<double>& x) {
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    for (int i = k + 1; i < n; ++i)
+      if (std::fabs(a[(size_t)i * n + k]) > std::fabs(a[(size_t)piv * n + k])) piv = i;
+    if (a[(size_t)piv * n + k] == 0.0) return false;
+    if (piv != k) {
+      for (int j = 0; j < n; ++j) std::swap(a[(size_t)k * n + j], a[(size_t)piv * n + j]);
+      std::swap(b[k], b[piv]);
+    }
+    for (int i = k + 1; i < n; ++i) {
+      const double f = a[(size_t)i * n + k] / a[(size_t)k * n + k];
+      if (f == 0.0) continue;
+      for (int j = k; j < n; ++j) a[(size_t)i * n + j] -= f * a[(size_t)k * n + j];
+      b[i] -= f * b[k];
+    }
+  }
+  x.assign(n, 0.0);
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int j = i + 1; j < n; ++j) s -= a[(size_t)i * n + j] * x[j];
+    x[i] = s / a[(size_t)i * n + i];
+  }
+  return true;
+}
+
+// c = solution of H c = (1,0,...,0) with the pseudo-inverse fallback of pyscf/lib/diis.py:extrapolate
+static std::vector<double> diis_coefficients(const std::vector<double>& Hfull, int ldh, int nd) {
+  const int m = nd + 1;
+  std::vector<double> h((size_t)m * m), g(m, 0.0), w, v, c;
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) h[(size_t)i * m + j] = Hfull[(size_t)i * ldh + j];
+  g[0] = 1.0;
+  jacobi_eigh(m, h, w, v);
+  bool singular = false;
+  for (int i = 0; i < m; ++i)
+    if (std::fabs(w[i]) < 1e-14) singular = true;
+  if (!singular && lu_solve(m, h, g, c)) return c;
+  c.assign(m, 0.0);
+  for (int k = 0; k < m; ++k) {
+    if (std::fabs(w[k]) <= 1e-14) continue;
+    double proj = 0.0;
+    for (int i = 0; i < m; ++i) proj += v[(size_t)i * m + k] * g[i];
+    for (int i = 0; i < m; ++i) c[i] += v[(size_t)i * m + k] * proj / w[k];
+  }
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Context
+// ------------------------------------------------------------------------------------------------
+struct DiisState {
+  // pyscf/lib/diis.py:DIIS bookkeeping (space = 6 for the Huzinaga loop, 8 for CDIIS on the mu path)
+  int space = 6;
+  int head = 0;
+  std::vector<int> bookkeep;
+  std::vector<double> H;  // (space+1)^2
+  bool have_xprev = false;
+  bool err_mode = false;  // true: error vectors are pushed explicitly (CDIIS)
+  DBuf<double> x, e, xprev, xnew;
+  long len = 0;
+  void init(int space_, long len_, bool err_mode_) {
+    space = space_;
+    len = len_;
+    err_mode = err_mode_;
+    head = 0;
+    bookkeep.clear();
+    H.assign((size_t)(space + 1) * (space + 1), 0.0);
+    for (int i = 1; i <= space; ++i) H[i] = H[(size_t)i * (space + 1)] = 1.0;
+    have_xprev = false;
+    x.ensure((size_t)space * len);
+    e.ensure((size_t)space * len);
+    xprev.ensure(len);
+    xnew.ensure(len);
+  }
+};
+
+struct nbd_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+  std::string err;
+  long launches = 0;
+  StageTimers timers;
+  int jk_variant = 0, gemm_variant = 0;
+  long x_budget_bytes = 3L << 30;  // workspace bound for the half-transformed tensor (aux-chunked)
+  int sm_count = 148;
+  size_t smem_optin = 0;
+
+  // ---- NCCL ----
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+
+  // ---- 3-centre tensor ----
+  int nao = 0, nb = 0, n_ld = 0, ntiles = 0, naux = 0;
+  long npair = 0;
+  double* Bt = nullptr;
+  std::vector<int> seq, inv;
+  DBuf<int> d_seq, d_inv;
+  DBuf<double> stage;  // packed-row staging for upload / download
+  PinnedBuf pinned;
+
+  // ---- J/K workspaces ----
+  DBuf<double> d_orb, d_wt, d_X, d_rho, d_jpart, d_jk;  // d_jk = [J sets | K sets] contiguous (all-reduce buffer)
+  DBuf<int> d_setbegin;
+
+  // ---- SCF problem ----
+  bool scf_ready = false;
+  int nspin = 0, projector = 0;
+  int nelec[2] = {0, 0};
+  double mu = 0.0;
+  DBuf<double> S, Xh, hcore, heff, GS, F, Huz, vhf, FG, T1, T2, Ct, D, Dold, evals, eigwork, red_part, red_out, Corth,
+      Ssave, dm0f;
+  DBuf<int> devinfo;
+  DiisState diis;
+  // bench state
+  bool bench_ready = false;
+  double bench_eprev[2] = {0, 0};
+
+  // ---- ao2mo ----
+  DBuf<double> mo_c, Lbuf, eri, eri_phys;
+};
+
+#define LAUNCH_CHECK(ctx)               \
+  do {                                  \
+    ++(ctx)->launches;                  \
+    NBD_CUDA(cudaGetLastError());       \
+  } while (0)
+
+static inline dim3 grid1(long cnt, int block) { return dim3((unsigned)((cnt + block - 1) / block)); }
+
+// ------------------------------------------------------------------------------------------------
+// GEMM wrappers (row-major views on top of gemm.cuh's stride-generic kernel)
+// ------------------------------------------------------------------------------------------------
+static void gemm(nbd_ctx* c, int M, int N, int K, const double* A, long a_is, long a_ks, const double* B, long b_js,
+                 long b_ks, double* C, long ldc, double alpha, double beta, int batch = 1, long sA = 0, long sB = 0,
+                 long sC = 0, int lower = 0, int a_kb = 0, long a_kos = 0, int b_kb = 0, long b_kos = 0) {
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.a_is = a_is; g.a_ks = a_ks; g.a_kb = a_kb; g.a_kos = a_kos;
+  g.B = B; g.b_js = b_js; g.b_ks = b_ks; g.b_kb = b_kb; g.b_kos = b_kos;
+  g.C = C; g.ldc = ldc; g.alpha = alpha; g.beta = beta;
+  g.batch = batch; g.strideA = sA; g.strideB = sB; g.strideC = sC; g.lower_only = lower;
+  NBD_CUDA(launch_gemm(c->stream, g, c->gemm_variant, &c->launches));
+}
+// C[M][N] = alpha * A[M][K] * B[K][N] + beta * C   (all row-major, leading dimensions given)
+static void gemm_nn(nbd_ctx* c, int M, int N, int K, const double* A, long lda, const double* B, long ldb, double* C,
+                    long ldc, double alpha = 1.0, double beta = 0.0, int batch = 1, long sA = 0, long sB = 0, long sC = 0) {
+  gemm(c, M, N, K, A, lda, 1, B, 1, ldb, C, ldc, alpha, beta, batch, sA, sB, sC);
+}
+// C = alpha * A^T * B: A stored [K][M]
+static void gemm_tn(nbd_ctx* c, int M, int N, int K, const double* A, long lda, const double* B, long ldb, double* C,
+                    long ldc, double alpha = 1.0, double beta = 0.0, int batch = 1, long sA = 0, long sB = 0, long sC = 0,
+                    int lower = 0) {
+  gemm(c, M, N, K, A, 1, lda, B, 1, ldb, C, ldc, alpha, beta, batch, sA, sB, sC, lower);
+}
+// C = alpha * A * B^T: B stored [N][K]
+static void gemm_nt(nbd_ctx* c, int M, int N, int K, const double* A, long lda, const double* B, long ldb, double* C,
+                    long ldc, double alpha = 1.0, double beta = 0.0, int batch = 1, long sA = 0, long sB = 0, long sC = 0) {
+  gemm(c, M, N, K, A, lda, 1, B, ldb, 1, C, ldc, alpha, beta, batch, sA, sB, sC);
+}
+
+static void symmetrize_lower(nbd_ctx* c, double* A, int n, int batch) {
+  dim3 g((n + 127) / 128, n, batch);
+  symmetrize_lower_kernel<<<g, 128, 0, c->stream>>>(A, n, (long)n * n);
+  LAUNCH_CHECK(c);
+}
+
+static void all_reduce(nbd_ctx* c, double* buf, size_t count) {
+  if (c->world <= 1 || !c->comm) return;
+  StageScope ts(c->timers, c->stream, "allreduce");
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->stream);
+  if (r != ncclSuccess) fail(NBD_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+}
+
+// ------------------------------------------------------------------------------------------------
+// J/K on device-resident orbitals
+// ------------------------------------------------------------------------------------------------
+struct KGroup {
+  int set;       // which K matrix
+  int c0, c1;    // columns [c0, c1) of the orbital block
+  double alpha;  // +1 / -1 (signed eigen-factors of a dense density)
+};
+
+template <int NSLOT, int NB>
+static void launch_symm_panel(nbd_ctx* c, const XArgs& a, int grid, size_t smem) {
+  auto kern = symm_panel_kernel<NSLOT, NB>;
+  NBD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, XK_THREADS, smem, c->stream>>>(a);
+  LAUNCH_CHECK(c);
+}
+
+// X[p][i][mu] for aux rows [p0, p0+np) and all Ntot orbital rows of d_orb ([Ntot][n_ld]).
+static void half_transform(nbd_ctx* c, int p0, int np, const double* d_orb, int Ntot, double* d_X) {
+  if (c->jk_variant == 1) {
+    dim3 g(c->nb, np);
+    symm_panel_simple_kernel<<<g, 256, 0, c->stream>>>(c->Bt + (long)p0 * c->ntiles * TILE_ELEMS, c->d_inv.p, d_orb,
+                                                        d_X, c->ntiles, c->nb, c->n_ld, Ntot);
+    LAUNCH_CHECK(c);
+    return;
+  }
+  const int nslot = (c->nb + 7) / 8;
+  NBD_REQUIRE(nslot <= 12, NBD_ERR_UNSUPPORTED, "nao = %d exceeds the 3072-AO envelope of the panel kernel", c->nao);
+  auto smem_for = [&](int ncolmax, int stages) {
+    const size_t ct = (((size_t)(ncolmax + 1) * (c->n_ld + 4) * 8) + 127) & ~(size_t)127;
+    return (size_t)256 + ct + (size_t)stages * TILE_BYTES;
+  };
+  int NBsel = (Ntot > 8 && nslot <= 6) ? 2 : 1;
+  if (NBsel == 2 && smem_for(16, 4) > c->smem_optin) NBsel = 1;
+  const int ncolmax = 8 * NBsel;
+  NBD_REQUIRE(smem_for(ncolmax, 2) <= c->smem_optin, NBD_ERR_UNSUPPORTED, "nao = %d: orbital slice does not fit shared memory", c->nao);
+  int stages = 16;
+  while (stages > 2 && smem_for(ncolmax, stages) > c->smem_optin) --stages;
+  XArgs a{};
+  a.Bt = c->Bt + (long)p0 * c->ntiles * TILE_ELEMS;
+  a.seq = c->d_seq.p;
+  a.Ct = d_orb;
+  a.X = d_X;
+  a.naux = np;
+  a.ntiles = c->ntiles;
+  a.nb = c->nb;
+  a.n_ld = c->n_ld;
+  a.Ntot = Ntot;
+  a.nslices = (Ntot + ncolmax - 1) / ncolmax;
+  a.nstages = stages;
+  const long nitems = (long)np * a.nslices;
+  long grid = std::min<long>(nitems, (long)c->sm_count);
+  // gridDim.x must be a multiple of nslices so that a CTA keeps the same orbital slice for all its items
+  grid = std::max<long>(a.nslices, grid / a.nslices * a.nslices);
+  const size_t smem = smem_for(ncolmax, stages);
+#define NBD_XK(NS, NBB) launch_symm_panel<NS, NBB>(c, a, (int)grid, smem)
+  if (NBsel == 2) {
+    if (nslot <= 1) NBD_XK(1, 2);
+    else if (nslot <= 2) NBD_XK(2, 2);
+    else if (nslot <= 4) NBD_XK(4, 2);
+    else NBD_XK(6, 2);
+  } else {
+    if (nslot <= 1) NBD_XK(1, 1);
+    else if (nslot <= 2) NBD_XK(2, 1);
+    else if (nslot <= 4) NBD_XK(4, 1);
+    else if (nslot <= 6) NBD_XK(6, 1);
+    else if (nslot <= 8) NBD_XK(8, 1);
+    else NBD_XK(12, 1);
+  }
+#undef NBD_XK
+}
+
+// d_orb [Ntot][n_ld] (scaled orbitals), d_wt [Ntot][n_ld] (= sign * orbitals).
+// J sets: jbegin[0..njset] column boundaries -> d_J [njset][n][n];  K groups -> d_K [nkset][n][n].
+// Either output may be null.  Results are all-reduced over the communicator when both live in c->d_jk.
+static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int Ntot, int njset,
+                      const std::vector<int>& jbegin, double* d_J, int nkset, const std::vector<KGroup>& kgroups,
+                      double* d_K) {
+  NBD_REQUIRE(c->Bt != nullptr, NBD_ERR_STATE, "J/K requested before the 3-centre tensor was allocated");
+  const int n = c->nao, n_ld = c->n_ld, naux = c->naux;
+  const long nn = (long)n * n;
+  StageScope ts_total(c->timers, c->stream, "jk_total");
+  if (d_K) NBD_CUDA(cudaMemsetAsync(d_K, 0, sizeof(double) * nn * nkset, c->stream));
+  if (d_J) NBD_CUDA(cudaMemsetAsync(d_J, 0, sizeof(double) * nn * njset, c->stream));
+  if (Ntot == 0 || naux == 0) return;
+  // aux chunking bounds the half-transformed tensor
+  const long per_row = (long)Ntot * n_ld * 8;
+  int chunk = (int)std::max<long>(1, std::min<long>(naux, c->x_budget_bytes / per_row));
+  double* X = c->d_X.ensure((size_t)chunk * Ntot * n_ld);
+  double* rho = c->d_rho.ensure((size_t)std::max(1, njset) * naux);
+  if (d_J) {
+    c->d_setbegin.ensure(njset + 1);
+    NBD_CUDA(cudaMemcpyAsync(c->d_setbegin.p, jbegin.data(), sizeof(int) * (njset + 1), cudaMemcpyHostToDevice, c->stream));
+  }
+  std::vector<bool> k_started(nkset, false);
+  for (int p0 = 0; p0 < naux; p0 += chunk) {
+    const int np = std::min(chunk, naux - p0);
+    {
+      StageScope ts(c->timers, c->stream, "jk_x");
+      half_transform(c, p0, np, d_orb, Ntot, X);
+    }
+    if (d_J) {
+      StageScope ts(c->timers, c->stream, "jk_rho");
+      rho_kernel<<<np, 256, 0, c->stream>>>(X, d_wt, rho + p0, naux, n_ld, Ntot, njset, c->d_setbegin.p, 0);
+      LAUNCH_CHECK(c);
+    }
+    if (d_K) {
+      StageScope ts(c->timers, c->stream, "jk_k");
+      // batch consecutive groups of identical width / sign belonging to consecutive sets into one launch
+      size_t gi = 0;
+      while (gi < kgroups.size()) {
+        const KGroup& g0 = kgroups[gi];
+        const int w = g0.c1 - g0.c0;
+        size_t gj = gi + 1;
+        while (gj < kgroups.size() && kgroups[gj].c1 - kgroups[gj].c0 == w && kgroups[gj].alpha == g0.alpha &&
+               kgroups[gj].set == kgroups[gj - 1].set + 1 && kgroups[gj].c0 == kgroups[gj - 1].c0 + w &&
+               k_started[kgroups[gj].set] == k_started[g0.set])
+          ++gj;
+        const int batch = (int)(gj - gi);
+        if (w > 0) {
+          const double* Xa = X + (long)g0.c0 * n_ld;
+          gemm(c, n, n, np * w, Xa, 1, n_ld, Xa, 1, n_ld, d_K + (long)g0.set * nn, n, g0.alpha,
+               k_started[g0.set] ? 1.0 : 0.0, batch, (long)w * n_ld, (long)w * n_ld, nn, /*lower=*/1, w,
+               (long)Ntot * n_ld, w, (long)Ntot * n_ld);
+          for (size_t q = gi; q < gj; ++q) k_started[kgroups[q].set] = true;
+        }
+        gi = gj;
+      }
+    }
+  }
+  if (d_J) {
+    StageScope ts(c->timers, c->stream, "jk_j");
+    const long E = (long)c->ntiles * TILE_ELEMS, E2 = E / 2;
+    const int bx = (int)((E2 + 255) / 256);
+    int nsplit = (int)std::min<long>(std::min(naux, 64), std::max<long>(1, ((long)c->sm_count * 16 + bx - 1) / bx));
+    const int rows_per_split = (naux + nsplit - 1) / nsplit;
+    nsplit = (naux + rows_per_split - 1) / rows_per_split;
+    for (int s0 = 0; s0 < njset; s0 += 2) {
+      const int ns = std::min(2, njset - s0);
+      double* part = c->d_jpart.ensure((size_t)nsplit * ns * E);
+      dim3 g(bx, nsplit);
+      if (ns == 2)
+        j_pass_kernel<2><<<g, 256, 0, c->stream>>>((const double2*)c->Bt, rho + (long)s0 * naux, (double2*)part, E2, naux, rows_per_split);
+      else
+        j_pass_kernel<1><<<g, 256, 0, c->stream>>>((const double2*)c->Bt, rho + (long)s0 * naux, (double2*)part, E2, naux, rows_per_split);
+      LAUNCH_CHECK(c);
+      dim3 gf((n + 127) / 128, n);
+      j_finalize_kernel<<<gf, 128, 0, c->stream>>>(part, c->d_inv.p, d_J + (long)s0 * nn, n, c->nb, E, nsplit, ns);
+      LAUNCH_CHECK(c);
+    }
+  }
+  if (d_K) symmetrize_lower(c, d_K, n, nkset);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reductions
+// ------------------------------------------------------------------------------------------------
+// out[slot] = reduce(a, b) ; mode as reduce_partial_kernel
+static void reduce_to(nbd_ctx* c, const double* a, const double* b, long cnt, int mode, int n, double* d_out) {
+  double* part = c->red_part.ensure(REDUCE_BLOCKS);
+  reduce_partial_kernel<<<REDUCE_BLOCKS, 256, 0, c->stream>>>(a, b, cnt, mode, n, part);
+  LAUNCH_CHECK(c);
+  reduce_final_kernel<<<1, 256, 0, c->stream>>>(part, REDUCE_BLOCKS, d_out);
+  LAUNCH_CHECK(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Eigensolvers (cuSOLVER; timed under "eigh")
+// ------------------------------------------------------------------------------------------------
+// A [batch][n][n] symmetric (row-major == column-major); on return rows of A = eigenvectors; w ascending.
+static void eigh_batched(nbd_ctx* c, double* A, double* w, int n, int batch) {
+  StageScope ts(c->timers, c->stream, "eigh");
+  int lwork = 0;
+  // numpy.linalg.eigh reads the lower triangle of the row-major matrix == the UPPER triangle column-major
+  NBD_SOLVER(cusolverDnDsyevd_bufferSize(c->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A, n, w, &lwork));
+  double* work = c->eigwork.ensure((size_t)lwork);
+  int* info = c->devinfo.ensure(8);
+  for (int b = 0; b < batch; ++b)
+    NBD_SOLVER(cusolverDnDsyevd(c->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A + (long)b * n * n, n,
+                                w + (long)b * n, work, lwork, info + b));
+}
+// generalised A x = w B x (scipy.linalg.eigh(f, s)); Bm is overwritten by its Cholesky factor.
+static void eigh_generalized(nbd_ctx* c, double* A, double* Bm, double* w, int n) {
+  StageScope ts(c->timers, c->stream, "eigh");
+  int lwork = 0;
+  NBD_SOLVER(cusolverDnDsygvd_bufferSize(c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A, n, Bm, n, w, &lwork));
+  double* work = c->eigwork.ensure((size_t)lwork);
+  int* info = c->devinfo.ensure(8);
+  NBD_SOLVER(cusolverDnDsygvd(c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A, n, Bm, n, w, work, lwork, info));
+}
+static void check_devinfo(nbd_ctx* c, int count, const char* what) {
+  int h[8] = {0};
+  NBD_CUDA(cudaMemcpyAsync(h, c->devinfo.p, sizeof(int) * count, cudaMemcpyDeviceToHost, c->stream));
+  NBD_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < count; ++i)
+    if (h[i] != 0) fail(NBD_ERR_CUDA, "%s: cuSOLVER devInfo = %d", what, h[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI helpers
+// ------------------------------------------------------------------------------------------------
+template <class F>
+static int guarded(nbd_ctx* ctx, F&& f) {
+  if (!ctx) return NBD_ERR_ARG;
+  try {
+    NBD_CUDA(cudaSetDevice(ctx->device));
+    f();
+    return NBD_OK;
+  } catch (const Error& e) {
+    ctx->err = e.msg;
+    ctx->timers.resolve();
+    return e.code;
+  } catch (const std::exception& e) {
+    ctx->err = e.what();
+    return NBD_ERR_CUDA;
+  }
+}
+static void finish_call(nbd_ctx* c) {
+  NBD_CUDA(cudaStreamSynchronize(c->stream));
+  c->timers.resolve();
+}
+static void h2d(nbd_ctx* c, double* dst, const double* src, size_t count) {
+  NBD_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+}
+static void d2h(nbd_ctx* c, double* dst, const double* src, size_t count) {
+  NBD_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+}
+
+extern "C" {
+
+int nbd_version(void) { return 100; }
+
+int nbd_create(nbd_ctx** out, int device) {
+  if (!out) return NBD_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return NBD_ERR_CUDA;
+  nbd_ctx* c = new nbd_ctx();
+  c->device = device;
+  try {
+    NBD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NBD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) fail(NBD_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    NBD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    NBD_SOLVER(cusolverDnCreate(&c->solver));
+    NBD_SOLVER(cusolverDnSetStream(c->solver, c->stream));
+  } catch (const Error& e) {
+    fprintf(stderr, "nbd_create: %s\n", e.msg.c_str());
+    int code = e.code;
+    delete c;
+    return code;
+  }
+  *out = c;
+  return NBD_OK;
+}
+
+int nbd_destroy(nbd_ctx* c) {
+  if (!c) return NBD_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->Bt) cudaFree(c->Bt);
+  if (c->solver) cusolverDnDestroy(c->solver);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return NBD_OK;
+}
+
+const char* nbd_last_error(nbd_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int nbd_set_option(nbd_ctx* c, const char* key, long value) {
+  if (!c || !key) return NBD_ERR_ARG;
+  std::string k(key);
+  if (k == "jk_variant") c->jk_variant = (int)value;
+  else if (k == "gemm_variant") c->gemm_variant = (int)value;
+  else if (k == "x_budget_mb") c->x_budget_bytes = value << 20;
+  else if (k == "timers") c->timers.enabled = value != 0;
+  else return NBD_ERR_ARG;
+  return NBD_OK;
+}
+
+double nbd_timer_ms(nbd_ctx* c, const char* key) {
+  if (!c || !key) return -1.0;
+  auto it = c->timers.ms.find(key);
+  return it == c->timers.ms.end() ? 0.0 : it->second;
+}
+
+long nbd_launch_count(nbd_ctx* c) { return c ? c->launches : -1; }
+
+// ---- NCCL ---------------------------------------------------------------------------------------
+int nbd_comm_unique_id(void* unique_id_128) {
+  std::string why;
+  if (!unique_id_128 || !g_nccl.load(why)) return NBD_ERR_CUDA;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return NBD_ERR_CUDA;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(unique_id_128, &id, 128);
+  return NBD_OK;
+}
+
+int nbd_comm_init(nbd_ctx* c, const void* unique_id_128, int rank, int world) {
+  return guarded(c, [&] {
+    NBD_REQUIRE(unique_id_128 && world >= 1 && rank >= 0 && rank < world, NBD_ERR_ARG, "bad communicator arguments");
+    std::string why;
+    if (!g_nccl.load(why)) fail(NBD_ERR_CUDA, "%s", why.c_str());
+    ncclUniqueId id;
+    memcpy(&id, unique_id_128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) fail(NBD_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    c->rank = rank;
+    c->world = world;
+  });
+}
+
+// ---- 3-centre tensor ------------------------------------------------------------------------------
+int nbd_cderi_alloc(nbd_ctx* c, int nao, int naux_local) {
+  return guarded(c, [&] {
+    NBD_REQUIRE(nao > 0 && naux_local >= 0, NBD_ERR_ARG, "nao = %d, naux = %d", nao, naux_local);
+    NBD_REQUIRE(naux_local <= 65535, NBD_ERR_UNSUPPORTED, "naux_local = %d > 65535", naux_local);
+    if (c->Bt) {
+      NBD_CUDA(cudaFree(c->Bt));
+      c->Bt = nullptr;
+    }
+    c->nao = nao;
+    c->nb = (nao + TILE - 1) / TILE;
+    c->n_ld = c->nb * TILE;
+    c->ntiles = c->nb * (c->nb + 1) / 2;
+    c->npair = (long)nao * (nao + 1) / 2;
+    c->naux = naux_local;
+    c->seq = build_tile_sequence(c->nb);
+    NBD_REQUIRE((int)c->seq.size() == c->ntiles, NBD_ERR_STATE, "tile sequence has %zu entries, expected %d", c->seq.size(), c->ntiles);
+    c->inv.assign((size_t)c->nb * c->nb, -1);
+    for (int k = 0; k < c->ntiles; ++k) c->inv[(size_t)(c->seq[k] >> 16) * c->nb + (c->seq[k] & 0xffff)] = k;
+    c->d_seq.ensure(c->ntiles);
+    c->d_inv.ensure((size_t)c->nb * c->nb);
+    NBD_CUDA(cudaMemcpyAsync(c->d_seq.p, c->seq.data(), sizeof(int) * c->ntiles, cudaMemcpyHostToDevice, c->stream));
+    NBD_CUDA(cudaMemcpyAsync(c->d_inv.p, c->inv.data(), sizeof(int) * c->nb * c->nb, cudaMemcpyHostToDevice, c->stream));
+    const size_t bytes = (size_t)std::max(1, naux_local) * c->ntiles * TILE_BYTES;
+    NBD_CUDA(cudaMalloc(&c->Bt, bytes));
+    c->scf_ready = false;
+    c->bench_ready = false;
+    finish_call(c);
+  });
+}
+
+static int stage_rows(nbd_ctx* c) {
+  const long budget = 256L << 20;
+  return (int)std::max<long>(1, std::min<long>(4096, budget / (c->npair * 8)));
+}
+
+int nbd_cderi_upload(nbd_ctx* c, const double* rows, int row0, int nrows) {
+  return guarded(c, [&] {
+    NBD_REQUIRE(c->Bt, NBD_ERR_STATE, "nbd_cderi_alloc first");
+    NBD_REQUIRE(rows && row0 >= 0 && nrows >= 0 && row0 + nrows <= c->naux, NBD_ERR_ARG, "rows [%d, %d) outside [0, %d)", row0, row0 + nrows, c->naux);
+    const int step = stage_rows(c);
+    double* st = c->stage.ensure((size_t)step * c->npair);
+    for (int r = 0; r < nrows; r += step) {
+      const int k = std::min(step, nrows - r);
+      h2d(c, st, rows + (long)r * c->npair, (size_t)k * c->npair);
+      dim3 g(c->ntiles, k);
+      pack_to_tiled_kernel<<<g, 256, 0, c->stream>>>(st, c->Bt, c->d_seq.p, c->ntiles, c->nao, c->npair, row0 + r);
+      LAUNCH_CHECK(c);
+      NBD_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    finish_call(c);
+  });
+}
+
+int nbd_cderi_synth(nbd_ctx* c, unsigned long long seed, double scale, int global_row0) {
+  return guarded(c, [&] {
+    NBD_REQUIRE(c->Bt, NBD_ERR_STATE, "nbd_cderi_alloc first");
+    if (c->naux > 0) {
+      dim3 g(c->ntiles, c->naux);
+      synth_tiled_kernel<<<g, 256, 0, c->stream>>>(c->Bt, c->d_seq.p, c->ntiles, c->nao, c->npair, seed, scale, global_row0);
+      LAUNCH_CHECK(c);
+    }
+    finish_call(c);
+  });
+}
+
+int nbd_cderi_download(nbd_ctx* c, double* rows, int row0, int nrows) {
+  return guarded(c, [&] {
+    NBD_REQUIRE(c->Bt, NBD_ERR_STATE, "nbd_cderi_alloc first");
+    NBD_REQUIRE(rows && row0 >= 0 && nrows >= 0 && row0 + nrows <= c->naux, NBD_ERR_ARG, "rows [%d, %d) outside [0, %d)", row0, row0 + nrows, c->naux);
+    const int step = stage_rows(c);
+    double* st = c->stage.ensure((size_t)step * c->npair);
+    for (int r = 0; r < nrows; r += step) {
+      const int k = std::min(step, nrows - r);
+      dim3 g(c->ntiles, k);
+      tiled_to_packed_kernel<<<g, 256, 0, c->stream>>>(c->Bt, st, c->d_seq.p, c->ntiles, c->nao, c->npair, row0 + r);
+      LAUNCH_CHECK(c);
+      d2h(c, rows + (long)r * c->npair, st, (size_t)k * c->npair);
+      NBD_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    finish_call(c);
+  });
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Host-orbital J/K (nbd_jk) and dense-density J/K (nbd_jk_dm)
+// ------------------------------------------------------------------------------------------------
+// d_src: device [ncols][src_ld] orbital rows (row = orbital); writes rows [row0, row0+ncols) of c->d_orb / c->d_wt.
+static void stage_orbitals(nbd_ctx* c, const double* d_src, long src_ld, int ncols, int row0, double fixed_scale,
+                           const double* d_rowscale, double wt_sign) {
+  if (ncols <= 0) return;
+  dim3 g((c->n_ld + 127) / 128, ncols);
+  pad_rows_kernel<<<g, 128, 0, c->stream>>>(d_src, src_ld, c->d_orb.p + (long)row0 * c->n_ld, c->n_ld, c->nao, d_rowscale, fixed_scale);
+  LAUNCH_CHECK(c);
+  pad_rows_kernel<<<g, 128, 0, c->stream>>>(d_src, src_ld, c->d_wt.p + (long)row0 * c->n_ld, c->n_ld, c->nao, d_rowscale, fixed_scale * wt_sign);
+  LAUNCH_CHECK(c);
+}
+
+extern "C" int nbd_jk(nbd_ctx* c, int nset, const int* ncol, const double* orb, const double* sign, double* vj, double* vk) {
+  return guarded(c, [&] {
+    c->timers.reset();
+    NBD_REQUIRE(c->Bt, NBD_ERR_STATE, "nbd_cderi_alloc first");
+    NBD_REQUIRE(nset >= 1 && nset <= 64 && ncol && orb, NBD_ERR_ARG, "bad nset / pointers");
+    const int n = c->nao;
+    const long nn = (long)n * n;
+    int Ntot = 0;
+    for (int s = 0; s < nset; ++s) {
+      NBD_REQUIRE(ncol[s] >= 0, NBD_ERR_ARG, "negative column count");
+      Ntot += ncol[s];
+    }
+    // host -> device with the columns of each set reordered: positive-sign columns first, then negative ones
+    c->d_orb.ensure((size_t)std::max(1, Ntot) * c->n_ld);
+    c->d_wt.ensure((size_t)std::max(1, Ntot) * c->n_ld);
+    std::vector<int> jbegin(nset + 1, 0);
+    std::vector<KGroup> groups;
+    std::vector<double> hrows((size_t)std::max(1, Ntot) * n), hsign(std::max(1, Ntot), 1.0);
+    {
+      long off = 0;  // offset into orb (per set: [n][ncol[s]] row-major)
+      int row = 0, sidx = 0;
+      for (int s = 0; s < nset; ++s) {
+        const int w = ncol[s];
+        const int start = row;
+        for (int pass = 0; pass < 2; ++pass) {
+          const int r0 = row;
+          for (int i = 0; i < w; ++i) {
+            const double sg = sign ? sign[sidx + i] : 1.0;
+            if ((pass == 0) != (sg >= 0.0)) continue;
+            for (int m = 0; m < n; ++m) hrows[(size_t)row * n + m] = orb[off + (long)m * w + i];
+            hsign[row] = sg >= 0.0 ? 1.0 : -1.0;
+            ++row;
+          }
+          if (row > r0) groups.push_back(KGroup{s, r0, row, pass == 0 ? 1.0 : -1.0});
+        }
+        (void)start;
+        jbegin[s + 1] = row;
+        off += (long)n * w;
+        sidx += w;
+      }
+    }
+    double* d_stage = c->stage.ensure((size_t)std::max(1, Ntot) * n + std::max(1, Ntot));
+    if (Ntot > 0) {
+      h2d(c, d_stage, hrows.data(), (size_t)Ntot * n);
+      h2d(c, d_stage + (size_t)Ntot * n, hsign.data(), Ntot);
+      dim3 g((c->n_ld + 127) / 128, Ntot);
+      pad_rows_kernel<<<g, 128, 0, c->stream>>>(d_stage, n, c->d_orb.p, c->n_ld, n, nullptr, 1.0);
+      LAUNCH_CHECK(c);
+      pad_rows_kernel<<<g, 128, 0, c->stream>>>(d_stage, n, c->d_wt.p, c->n_ld, n, d_stage + (size_t)Ntot * n, 1.0);
+      LAUNCH_CHECK(c);
+    }
+    const int nj = vj ? nset : 0, nk = vk ? nset : 0;
+    double* buf = c->d_jk.ensure((size_t)std::max(1, nj + nk) * nn);
+    jk_device(c, c->d_orb.p, c->d_wt.p, Ntot, nj, jbegin, vj ? buf : nullptr, nk, groups, vk ? buf + (size_t)nj * nn : nullptr);
+    all_reduce(c, buf, (size_t)(nj + nk) * nn);
+    if (vj) d2h(c, vj, buf, (size_t)nj * nn);
+    if (vk) d2h(c, vk, buf + (size_t)nj * nn, (size_t)nk * nn);
+    finish_call(c);
+  });
+}
+
+// Factor symmetric dense densities dm[s] = sum_i sign_i c_i c_i^T (eigen-decomposition) into c->d_orb / c->d_wt.
+// d_dm: device [nset][n][n] (destroyed).  Returns Ntot and fills jbegin / groups.  tol drops |w| <= tol * max|w|.
+static int factor_densities(nbd_ctx* c, double* d_dm, int nset, std::vector<int>& jbegin, std::vector<KGroup>& groups) {
+  const int n = c->nao;
+  double* w = c->evals.ensure((size_t)nset * n);
+  eigh_batched(c, d_dm, w, n, nset);
+  std::vector<double> hw((size_t)nset * n);
+  d2h(c, hw.data(), w, (size_t)nset * n);
+  check_devinfo(c, std::min(nset, 8), "density factorisation");
+  // rows of d_dm are now eigenvectors; scale by sqrt|w| and keep the significant ones (ascending order:
+  // negatives first, positives last)
+  jbegin.assign(nset + 1, 0);
+  groups.clear();
+  int total = 0;
+  std::vector<std::array<int, 4>> plan;  // set, first row, count, sign
+  for (int s = 0; s < nset; ++s) {
+    double wmax = 0.0;
+    for (int i = 0; i < n; ++i) wmax = std::max(wmax, std::fabs(hw[(size_t)s * n + i]));
+    const double thr = wmax * 1e-14;
+    int nneg = 0, npos = 0;
+    for (int i = 0; i < n; ++i) {
+      const double v = hw[(size_t)s * n + i];
+      if (v < -thr) ++nneg;
+      else if (v > thr) ++npos;
+    }
+    // eigenvalues ascend: the first nneg rows are the negative ones, the last npos the positive ones
+    plan.push_back({s, n - npos, npos, +1});
+    plan.push_back({s, 0, nneg, -1});
+    total += npos + nneg;
+  }
+  c->d_orb.ensure((size_t)std::max(1, total) * c->n_ld);
+  c->d_wt.ensure((size_t)std::max(1, total) * c->n_ld);
+  int row = 0;
+  for (auto& pl : plan) {
+    const int s = pl[0], r0 = pl[1], cnt = pl[2], sg = pl[3];
+    if (cnt > 0) {
+      double* src = d_dm + (long)s * n * n + (long)r0 * n;
+      dim3 g((n + 127) / 128, cnt);
+      scale_rows_kernel<<<g, 128, 0, c->stream>>>(src, w + (long)s * n + r0, n, 1);
+      LAUNCH_CHECK(c);
+      stage_orbitals(c, src, n, cnt, row, 1.0, nullptr, (double)sg);
+      groups.push_back(KGroup{s, row, row + cnt, (double)sg});
+      row += cnt;
+    }
+    if (sg < 0) jbegin[s + 1] = row;
+  }
+  return total;
+}
+
+extern "C" int nbd_jk_dm(nbd_ctx* c, int nset, const double* dm, double* vj, double* vk) {
+  return guarded(c, [&] {
+    c->timers.reset();
+    NBD_REQUIRE(c->Bt, NBD_ERR_STATE, "nbd_cderi_alloc first");
+    NBD_REQUIRE(nset >= 1 && nset <= 8 && dm, NBD_ERR_ARG, "bad nset / pointers");
+    const int n = c->nao;
+    const long nn = (long)n * n;
+    double* d_dm = c->dm0f.ensure((size_t)nset * nn);
+    h2d(c, d_dm, dm, (size_t)nset * nn);
+    std::vector<int> jbegin;
+    std::vector<KGroup> groups;
+    const int Ntot = factor_densities(c, d_dm, nset, jbegin, groups);
+    const int nj = vj ? nset : 0, nk = vk ? nset : 0;
+    double* buf = c->d_jk.ensure((size_t)std::max(1, nj + nk) * nn);
+    jk_device(c, c->d_orb.p, c->d_wt.p, Ntot, nj, jbegin, vj ? buf : nullptr, nk, groups, vk ? buf + (size_t)nj * nn : nullptr);
+    all_reduce(c, buf, (size_t)(nj + nk) * nn);
+    if (vj) d2h(c, vj, buf, (size_t)nj * nn);
+    if (vk) d2h(c, vk, buf + (size_t)nj * nn, (size_t)nk * nn);
+    finish_call(c);
+  });
+}
+
+#include "scf_host.cuh"
+#include "ao2mo_host.cuh"

@@ -1,0 +1,524 @@
+// Embedded-SCF drivers behind the C-ABI: static set-up, the Huzinaga loop (nbed/scf/huzinaga_scf.py:93-206),
+// the mu-shift loop (pyscf.scf.hf.kernel as driven by nbed/driver.py:500-538) and the benchmark stepper.
+// Included by nbed_b200.cu (single translation unit).
+#pragma once
+
+// ---- helpers ------------------------------------------------------------------------------------
+static int scf_nocc(const nbd_ctx* c, int s) { return c->nspin == 2 ? c->nelec[s] : (c->nelec[0] + c->nelec[1]) / 2; }
+static double scf_occ(const nbd_ctx* c) { return c->nspin == 2 ? 1.0 : 2.0; }
+
+// occupied rows of Ct -> scaled orbital block for J/K;  returns Ntot
+static int scf_stage_occupied(nbd_ctx* c) {
+  const int n = c->nao;
+  int tot = 0;
+  for (int s = 0; s < c->nspin; ++s) tot += scf_nocc(c, s);
+  c->d_orb.ensure((size_t)std::max(1, tot) * c->n_ld);
+  c->d_wt.ensure((size_t)std::max(1, tot) * c->n_ld);
+  int row = 0;
+  for (int s = 0; s < c->nspin; ++s) {
+    const int o = scf_nocc(c, s);
+    stage_orbitals(c, c->Ct.p + (long)s * n * n, n, o, row, std::sqrt(scf_occ(c)), nullptr, 1.0);
+    row += o;
+  }
+  return tot;
+}
+
+// J/K of the staged orbital block -> vhf_s = J - kscale K_s and F_s = heff_s + vhf_s
+static void scf_build_fock(nbd_ctx* c, int Ntot, const std::vector<KGroup>& groups) {
+  const int n = c->nao;
+  const long nn = (long)n * n;
+  const int ns = c->nspin;
+  double* buf = c->d_jk.ensure((size_t)(1 + ns) * nn);
+  std::vector<int> jbegin = {0, Ntot};
+  jk_device(c, c->d_orb.p, c->d_wt.p, Ntot, 1, jbegin, buf, ns, groups, buf + nn);
+  all_reduce(c, buf, (size_t)(1 + ns) * nn);
+  StageScope ts(c->timers, c->stream, "fock");
+  fock_from_heff_kernel<<<grid1(nn, 256), 256, 0, c->stream>>>(c->heff.p, buf, buf + nn, ns == 2 ? 1.0 : 0.5, c->F.p, c->vhf.p, nn, ns);
+  LAUNCH_CHECK(c);
+}
+static std::vector<KGroup> scf_occ_groups(const nbd_ctx* c) {
+  std::vector<KGroup> g;
+  int row = 0;
+  for (int s = 0; s < c->nspin; ++s) {
+    const int o = scf_nocc(c, s);
+    g.push_back(KGroup{s, row, row + o, 1.0});
+    row += o;
+  }
+  return g;
+}
+
+// Huz_s = -cfac (F_s gammaS_s + (F_s gammaS_s)^T);  F_s += Huz_s      (huzinaga_scf.py:65-90,159-160)
+static void scf_apply_huzinaga(nbd_ctx* c) {
+  StageScope ts(c->timers, c->stream, "fock");
+  const int n = c->nao;
+  const long nn = (long)n * n;
+  gemm_nn(c, n, n, n, c->F.p, n, c->GS.p, n, c->FG.p, n, 1.0, 0.0, c->nspin, nn, nn, nn);
+  dim3 g((n + 31) / 32, (n + 31) / 32, c->nspin), b(32, 8);
+  huzinaga_apply_kernel<<<g, b, 0, c->stream>>>(c->FG.p, c->nspin == 2 ? 1.0 : 0.5, c->Huz.p, c->F.p, n);
+  LAUNCH_CHECK(c);
+}
+
+// F' = X F X ; eigh ; Ct = V X (rows = MOs)       (huzinaga_scf.py:166-169)
+static void scf_diagonalise_lowdin(nbd_ctx* c) {
+  const int n = c->nao;
+  const long nn = (long)n * n;
+  {
+    StageScope ts(c->timers, c->stream, "orth");
+    gemm_nn(c, n, n, n, c->F.p, n, c->Xh.p, n, c->T1.p, n, 1.0, 0.0, c->nspin, nn, 0, nn);
+    gemm_nn(c, n, n, n, c->Xh.p, n, c->T1.p, n, c->T2.p, n, 1.0, 0.0, c->nspin, 0, nn, nn);
+  }
+  eigh_batched(c, c->T2.p, c->evals.p, n, c->nspin);
+  {
+    StageScope ts(c->timers, c->stream, "orth");
+    gemm_nn(c, n, n, n, c->T2.p, n, c->Xh.p, n, c->Ct.p, n, 1.0, 0.0, c->nspin, nn, 0, nn);
+  }
+}
+
+// D_s = occ * sum_{i < o_s} c_i c_i^T  (old D kept in Dold)     (huzinaga_scf.py:170-174)
+static void scf_make_density(nbd_ctx* c) {
+  StageScope ts(c->timers, c->stream, "density");
+  const int n = c->nao;
+  const long nn = (long)n * n;
+  std::swap(c->D.p, c->Dold.p);
+  std::swap(c->D.cap, c->Dold.cap);
+  for (int s = 0; s < c->nspin; ++s) {
+    const int o = scf_nocc(c, s);
+    if (o == 0) {
+      NBD_CUDA(cudaMemsetAsync(c->D.p + s * nn, 0, sizeof(double) * nn, c->stream));
+      continue;
+    }
+    gemm_tn(c, n, n, o, c->Ct.p + s * nn, n, c->Ct.p + s * nn, n, c->D.p + s * nn, n, scf_occ(c), 0.0, 1, 0, 0, 0, /*lower=*/1);
+  }
+  symmetrize_lower(c, c->D.p, n, c->nspin);
+}
+
+// out8 (host) = per spin [a.D, b.D, c.D, |D - Dold|^2]
+static void scf_traces(nbd_ctx* c, const double* a, const double* b, const double* cc, bool with_dd, double* out8) {
+  StageScope ts(c->timers, c->stream, "energy");
+  const long nn = (long)c->nao * c->nao;
+  double* part = c->red_part.ensure((size_t)REDUCE_BLOCKS * 9);
+  double* out = c->red_out.ensure(64);
+  scf_traces_partial_kernel<<<REDUCE_BLOCKS, 256, 0, c->stream>>>(a, b, cc, c->D.p, with_dd ? c->Dold.p : nullptr, nn, c->nspin, part);
+  LAUNCH_CHECK(c);
+  scf_traces_final_kernel<<<1, 256, 0, c->stream>>>(part, REDUCE_BLOCKS, 4 * c->nspin, out);
+  LAUNCH_CHECK(c);
+  d2h(c, out8, out, 4 * c->nspin);
+  NBD_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// ---- DIIS (pyscf/lib/diis.py:DIIS.update; CDIIS pushes its own error vector) ------------------------
+// x: device vector of d.len doubles, overwritten with the extrapolated vector when one is produced.
+static void diis_update(nbd_ctx* c, DiisState& d, double* x, const double* errvec) {
+  StageScope ts(c->timers, c->stream, "diis");
+  const long len = d.len;
+  const size_t bytes = sizeof(double) * len;
+  if (errvec) {  // push_err_vec
+    if (d.head >= d.space) d.head = 0;
+    NBD_CUDA(cudaMemcpyAsync(d.e.p + (long)d.head * len, errvec, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  // push_vec
+  while ((int)d.bookkeep.size() >= d.space) d.bookkeep.erase(d.bookkeep.begin());
+  if (errvec) {
+    d.bookkeep.push_back(d.head);
+    NBD_CUDA(cudaMemcpyAsync(d.x.p + (long)d.head * len, x, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    d.head += 1;
+  } else if (!d.have_xprev) {
+    NBD_CUDA(cudaMemcpyAsync(d.xprev.p, x, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    d.have_xprev = true;
+  } else {
+    if (d.head >= d.space) d.head = 0;
+    d.bookkeep.push_back(d.head);
+    NBD_CUDA(cudaMemcpyAsync(d.x.p + (long)d.head * len, x, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    sub_kernel<<<grid1(len, 256), 256, 0, c->stream>>>(x, d.xprev.p, d.e.p + (long)d.head * len, len);
+    LAUNCH_CHECK(c);
+    d.head += 1;
+  }
+  const int nd = (int)d.bookkeep.size();
+  if (nd < 1) return;  // min_space = 1
+  // Gram row of the newest error vector against all stored ones
+  MultiDotArgs ma{};
+  ma.nd = nd;
+  for (int i = 0; i < nd; ++i) ma.ys[i] = d.e.p + (long)i * len;
+  double* part = c->red_part.ensure((size_t)REDUCE_BLOCKS * 9);
+  double* out = c->red_out.ensure(64);
+  multidot_partial_kernel<<<REDUCE_BLOCKS, 256, 0, c->stream>>>(d.e.p + (long)(d.head - 1) * len, ma, len, part);
+  LAUNCH_CHECK(c);
+  multidot_final_kernel<<<1, 256, 0, c->stream>>>(part, REDUCE_BLOCKS, nd, out + 16);
+  LAUNCH_CHECK(c);
+  double hrow[9];
+  d2h(c, hrow, out + 16, nd);
+  NBD_CUDA(cudaStreamSynchronize(c->stream));
+  const int ldh = d.space + 1;
+  for (int i = 0; i < nd; ++i) {
+    d.H[(size_t)d.head * ldh + i + 1] = hrow[i];
+    d.H[(size_t)(i + 1) * ldh + d.head] = hrow[i];
+  }
+  std::vector<double> coef = diis_coefficients(d.H, ldh, nd);
+  LinCombArgs la{};
+  la.nd = nd;
+  for (int i = 0; i < nd; ++i) {
+    la.xs[i] = d.x.p + (long)i * len;
+    la.coef[i] = coef[i + 1];
+  }
+  lincomb_kernel<<<grid1(len, 256), 256, 0, c->stream>>>(la, x, len);
+  LAUNCH_CHECK(c);
+  if (d.have_xprev) NBD_CUDA(cudaMemcpyAsync(d.xprev.p, x, bytes, cudaMemcpyDeviceToDevice, c->stream));
+}
+
+// ---- static set-up -----------------------------------------------------------------------------------
+extern "C" int nbd_scf_setup(nbd_ctx* c, int nspin, const int* nelec, const double* ovlp, const double* hcore,
+                             const double* v_emb, const double* dm_env, int projector, double mu) {
+  return guarded(c, [&] {
+    c->timers.reset();
+    NBD_REQUIRE(c->Bt, NBD_ERR_STATE, "nbd_cderi_alloc first (nao is taken from the 3-centre tensor)");
+    NBD_REQUIRE((nspin == 1 || nspin == 2) && nelec && ovlp && hcore && v_emb && dm_env, NBD_ERR_ARG, "bad nspin / pointers");
+    NBD_REQUIRE(projector == NBD_HUZINAGA || projector == NBD_MU_SHIFT, NBD_ERR_ARG, "unknown projector %d", projector);
+    const int n = c->nao;
+    const long nn = (long)n * n;
+    NBD_REQUIRE(nelec[0] >= 0 && nelec[1] >= 0 && nelec[0] <= n && nelec[1] <= n, NBD_ERR_ARG, "nelec out of range");
+    c->nspin = nspin;
+    c->nelec[0] = nelec[0];
+    c->nelec[1] = nelec[1];
+    c->projector = projector;
+    c->mu = mu;
+    c->S.ensure(nn); c->Xh.ensure(nn); c->hcore.ensure(nn);
+    for (DBuf<double>* b : {&c->heff, &c->GS, &c->F, &c->Huz, &c->vhf, &c->FG, &c->T1, &c->T2, &c->Ct, &c->D, &c->Dold, &c->Corth})
+      b->ensure((size_t)2 * nn);
+    c->evals.ensure((size_t)8 * n);
+    h2d(c, c->S.p, ovlp, nn);
+    h2d(c, c->hcore.p, hcore, nn);
+    h2d(c, c->T1.p, v_emb, (size_t)nspin * nn);   // V_emb
+    h2d(c, c->T2.p, dm_env, (size_t)nspin * nn);  // gamma_env
+    // X = S^-1/2 = (w^-1/4 V)^T (w^-1/4 V)     (huzinaga_scf.py:128)
+    NBD_CUDA(cudaMemcpyAsync(c->FG.p, c->S.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, c->stream));
+    eigh_batched(c, c->FG.p, c->evals.p, n, 1);
+    {
+      std::vector<double> w(n);
+      d2h(c, w.data(), c->evals.p, n);
+      check_devinfo(c, 1, "overlap eigendecomposition");
+      NBD_REQUIRE(w[0] > 0.0, NBD_ERR_ARG, "overlap matrix is not positive definite (lowest eigenvalue %g)", w[0]);
+    }
+    {
+      dim3 g((n + 127) / 128, n);
+      scale_rows_kernel<<<g, 128, 0, c->stream>>>(c->FG.p, c->evals.p, n, 2);
+      LAUNCH_CHECK(c);
+    }
+    gemm_tn(c, n, n, n, c->FG.p, n, c->FG.p, n, c->Xh.p, n, 1.0, 0.0, 1, 0, 0, 0, /*lower=*/1);
+    symmetrize_lower(c, c->Xh.p, n, 1);
+    // gamma S (huzinaga_scf.py:132)
+    gemm_nn(c, n, n, n, c->T2.p, n, c->S.p, n, c->GS.p, n, 1.0, 0.0, nspin, nn, 0, nn);
+    if (projector == NBD_MU_SHIFT) {
+      // P_s = S gamma_s S (driver.py:433-449); heff = h + V + mu P (driver.py:518,529)
+      gemm_nn(c, n, n, n, c->S.p, n, c->GS.p, n, c->FG.p, n, 1.0, 0.0, nspin, 0, nn, nn);
+      heff_kernel<<<grid1(nn, 256), 256, 0, c->stream>>>(c->hcore.p, c->T1.p, c->FG.p, mu, c->heff.p, nn, nspin);
+    } else {
+      heff_kernel<<<grid1(nn, 256), 256, 0, c->stream>>>(c->hcore.p, c->T1.p, nullptr, 0.0, c->heff.p, nn, nspin);
+    }
+    LAUNCH_CHECK(c);
+    c->scf_ready = true;
+    c->bench_ready = false;
+    finish_call(c);
+  });
+}
+
+// ---- Huzinaga loop -----------------------------------------------------------------------------------
+struct HuzLoop {
+  int Ntot = 0;
+  std::vector<KGroup> groups;
+  bool orbitals_from_guess = true;
+};
+
+// initial guess of huzinaga_scf.py:139-148 (dm0 == null) or a dense user density
+static void huz_initial(nbd_ctx* c, const double* dm0, HuzLoop& L) {
+  const int n = c->nao;
+  const long nn = (long)n * n;
+  if (!dm0) {
+    NBD_CUDA(cudaMemcpyAsync(c->F.p, c->heff.p, sizeof(double) * nn * c->nspin, cudaMemcpyDeviceToDevice, c->stream));
+    scf_apply_huzinaga(c);
+    scf_diagonalise_lowdin(c);
+    scf_make_density(c);
+    L.Ntot = scf_stage_occupied(c);
+    L.groups = scf_occ_groups(c);
+  } else {
+    h2d(c, c->D.p, dm0, (size_t)c->nspin * nn);
+    double* tmp = c->dm0f.ensure((size_t)c->nspin * nn);
+    NBD_CUDA(cudaMemcpyAsync(tmp, c->D.p, sizeof(double) * nn * c->nspin, cudaMemcpyDeviceToDevice, c->stream));
+    std::vector<int> jb;
+    L.Ntot = factor_densities(c, tmp, c->nspin, jb, L.groups);
+  }
+}
+
+// one pass of the loop body (huzinaga_scf.py:154-201); out: per-spin energies and max_s ||dD_s||_F
+static void huz_iteration(nbd_ctx* c, int iter, bool use_diis, HuzLoop& L, double* energy, double* norm_ddm) {
+  const long nn = (long)c->nao * c->nao;
+  scf_build_fock(c, L.Ntot, L.groups);                                // :156-157
+  scf_apply_huzinaga(c);                                              // :159-160
+  if (use_diis && iter > 1) diis_update(c, c->diis, c->F.p, nullptr);  // :162-164
+  scf_diagonalise_lowdin(c);                                          // :166-169
+  scf_make_density(c);                                                // :170-174
+  double t[8];
+  scf_traces(c, c->heff.p, c->vhf.p, c->Huz.p, true, t);              // :182-194
+  double nd = 0.0;
+  for (int s = 0; s < c->nspin; ++s) {
+    energy[s] = t[4 * s + 0] + 0.5 * t[4 * s + 1] + t[4 * s + 2];
+    nd = std::max(nd, std::sqrt(t[4 * s + 3]));
+  }
+  *norm_ddm = nd;
+  L.Ntot = scf_stage_occupied(c);
+  L.groups = scf_occ_groups(c);
+  (void)nn;
+}
+
+static void scf_export(nbd_ctx* c, double* mo_coeff, double* mo_energy, double* dm, double* extra, const double* d_extra) {
+  const int n = c->nao;
+  const long nn = (long)n * n;
+  if (mo_coeff) {
+    dim3 g((n + 31) / 32, (n + 31) / 32, c->nspin), b(32, 8);
+    transpose_kernel<<<g, b, 0, c->stream>>>(c->Ct.p, c->T1.p, n, n);
+    LAUNCH_CHECK(c);
+    d2h(c, mo_coeff, c->T1.p, (size_t)c->nspin * nn);
+  }
+  if (mo_energy) d2h(c, mo_energy, c->evals.p, (size_t)c->nspin * n);
+  if (dm) d2h(c, dm, c->D.p, (size_t)c->nspin * nn);
+  if (extra) d2h(c, extra, d_extra, (size_t)c->nspin * nn);
+}
+
+extern "C" int nbd_huzinaga_scf(nbd_ctx* c, int max_cycle, double conv_tol, double dm_conv_tol, int use_diis,
+                                const double* dm0, double* mo_coeff, double* mo_energy, double* dm, double* huz,
+                                double* trace, nbd_scf_result* result) {
+  return guarded(c, [&] {
+    c->timers.reset();
+    NBD_REQUIRE(c->scf_ready && c->projector == NBD_HUZINAGA, NBD_ERR_STATE, "nbd_scf_setup(projector = NBD_HUZINAGA) first");
+    NBD_REQUIRE(max_cycle >= 1, NBD_ERR_ARG, "max_cycle = %d", max_cycle);
+    const long nn = (long)c->nao * c->nao;
+    {
+    StageScope ts_all(c->timers, c->stream, "scf_total");
+    HuzLoop L;
+    huz_initial(c, dm0, L);
+    c->diis.init(6, c->nspin * nn, false);
+    double eprev[2] = {0.0, 0.0}, e[2] = {0.0, 0.0}, nd = 0.0;
+    int conv = 0, cycles = 0;
+    for (int i = 0; i < max_cycle; ++i) {
+      StageScope ts(c->timers, c->stream, "iter_total");
+      huz_iteration(c, i, use_diis != 0, L, e, &nd);
+      ++cycles;
+      double run_diff = 0.0;
+      for (int s = 0; s < c->nspin; ++s) run_diff = std::max(run_diff, std::fabs(e[s] - eprev[s]));
+      if (trace) {
+        trace[3 * i + 0] = e[0];
+        trace[3 * i + 1] = c->nspin == 2 ? e[1] : e[0];
+        trace[3 * i + 2] = nd;
+      }
+      if (run_diff < conv_tol && nd < dm_conv_tol) {  // :196
+        conv = 1;
+        break;
+      }
+      eprev[0] = e[0];
+      eprev[1] = e[1];
+    }
+    check_devinfo(c, c->nspin, "Fock eigendecomposition");
+    scf_export(c, mo_coeff, mo_energy, dm, huz, c->Huz.p);
+    if (result) {
+      result->converged = conv;
+      result->cycles = cycles;
+      result->energy[0] = e[0];
+      result->energy[1] = c->nspin == 2 ? e[1] : e[0];
+      result->e_tot = c->nspin == 2 ? e[0] + e[1] : e[0];
+      result->norm_ddm = nd;
+      result->norm_grad = 0.0;
+    }
+    }  // stop events of the scopes above are recorded before the final synchronize
+    finish_call(c);
+  });
+}
+
+// ---- benchmark stepper: the same loop body, one call per iteration --------------------------------------
+static HuzLoop g_bench_loop;  // per process (one context per process and GPU)
+
+extern "C" int nbd_scf_bench_init(nbd_ctx* c) {
+  return guarded(c, [&] {
+    c->timers.reset();
+    NBD_REQUIRE(c->scf_ready && c->projector == NBD_HUZINAGA, NBD_ERR_STATE, "nbd_scf_setup(projector = NBD_HUZINAGA) first");
+    const long nn = (long)c->nao * c->nao;
+    g_bench_loop = HuzLoop();
+    huz_initial(c, nullptr, g_bench_loop);
+    c->diis.init(6, c->nspin * nn, false);
+    c->bench_ready = true;
+    finish_call(c);
+  });
+}
+
+extern "C" int nbd_scf_bench_iteration(nbd_ctx* c, int iter, double* energy2, double* norm_ddm) {
+  int rc = guarded(c, [&] {
+    c->timers.reset();
+    NBD_REQUIRE(c->bench_ready, NBD_ERR_STATE, "nbd_scf_bench_init first");
+    double e[2] = {0, 0}, nd = 0;
+    {
+      StageScope ts(c->timers, c->stream, "iter_total");
+      huz_iteration(c, iter, true, g_bench_loop, e, &nd);
+    }
+    if (energy2) {
+      energy2[0] = e[0];
+      energy2[1] = c->nspin == 2 ? e[1] : e[0];
+    }
+    if (norm_ddm) *norm_ddm = nd;
+  });
+  if (rc == NBD_OK) rc = guarded(c, [&] { finish_call(c); });
+  return rc;
+}
+
+// ---- mu-shift loop ---------------------------------------------------------------------------------------
+// e_tot = e1 + e_coul + e_nuc with the spin-resolved core Hamiltonian (embedded_hcore_funcs.py:11-46)
+static double mu_energy(nbd_ctx* c, double e_nuc) {
+  double t[8];
+  scf_traces(c, c->heff.p, c->vhf.p, nullptr, false, t);
+  double e1 = 0.0, ec = 0.0;
+  for (int s = 0; s < c->nspin; ++s) {
+    e1 += t[4 * s + 0];
+    ec += t[4 * s + 1];
+  }
+  return e1 + 0.5 * ec + e_nuc;
+}
+
+// generalised eigensolve per spin of c->F (copied), rows of Ct = MOs
+static void mu_eig(nbd_ctx* c, const double* Fsrc, double* Crows) {
+  const int n = c->nao;
+  const long nn = (long)n * n;
+  for (int s = 0; s < c->nspin; ++s) {
+    NBD_CUDA(cudaMemcpyAsync(Crows + s * nn, Fsrc + s * nn, sizeof(double) * nn, cudaMemcpyDeviceToDevice, c->stream));
+    NBD_CUDA(cudaMemcpyAsync(c->Ssave.p, c->S.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, c->stream));
+    eigh_generalized(c, Crows + s * nn, c->Ssave.p, c->evals.p + (long)s * n, n);
+  }
+}
+
+// ||g||, g_s = C_vir^T F_s C_occ   (pyscf/scf/uhf.py:get_grad)
+static double mu_grad_norm(nbd_ctx* c) {
+  StageScope ts(c->timers, c->stream, "energy");
+  const int n = c->nao;
+  const long nn = (long)n * n;
+  double* out = c->red_out.ensure(64);
+  double tot = 0.0;
+  double h[2] = {0, 0};
+  for (int s = 0; s < c->nspin; ++s) {
+    const int o = scf_nocc(c, s), v = n - o;
+    if (o == 0 || v == 0) continue;
+    // T[i][mu] = sum_nu Ct[i][nu] F[nu][mu] ; G[a][i] = sum_mu Ct[o+a][mu] T[i][mu]
+    gemm_nn(c, o, n, n, c->Ct.p + s * nn, n, c->F.p + s * nn, n, c->T1.p, n);
+    gemm_nt(c, v, o, n, c->Ct.p + s * nn + (long)o * n, n, c->T1.p, n, c->T2.p, o);
+    reduce_to(c, c->T2.p, c->T2.p, (long)v * o, 0, n, out + 32 + s);
+  }
+  d2h(c, h, out + 32, 2);
+  NBD_CUDA(cudaStreamSynchronize(c->stream));
+  for (int s = 0; s < c->nspin; ++s) {
+    const int o = scf_nocc(c, s);
+    if (o == 0 || o == n) continue;
+    tot += h[s] * (c->nspin == 1 ? 4.0 : 1.0);  // RHF gradient carries a factor 2
+  }
+  return std::sqrt(tot);
+}
+
+// CDIIS error vector per spin: Corth^T (S D F) Corth, antisymmetrised (pyscf/scf/diis.py:get_err_vec_orth)
+static void mu_cdiis_errvec(nbd_ctx* c, double* err) {
+  StageScope ts(c->timers, c->stream, "diis");
+  const int n = c->nao;
+  const long nn = (long)n * n;
+  const int ns = c->nspin;
+  gemm_nn(c, n, n, n, c->S.p, n, c->D.p, n, c->T1.p, n, 1.0, 0.0, ns, 0, nn, nn);      // S D
+  gemm_nn(c, n, n, n, c->T1.p, n, c->F.p, n, c->T2.p, n, 1.0, 0.0, ns, nn, nn, nn);    // (S D) F
+  gemm_nn(c, n, n, n, c->Corth.p, n, c->T2.p, n, c->T1.p, n, 1.0, 0.0, ns, nn, nn, nn);  // Corth^T (.)   (rows = MOs)
+  gemm_nt(c, n, n, n, c->T1.p, n, c->Corth.p, n, c->T2.p, n, 1.0, 0.0, ns, nn, nn, nn);  // (.) Corth
+  dim3 g((n + 127) / 128, n, ns);
+  antisym_kernel<<<g, 128, 0, c->stream>>>(c->T2.p, err, n);
+  LAUNCH_CHECK(c);
+}
+
+extern "C" int nbd_mu_scf(nbd_ctx* c, int max_cycle, double conv_tol, double e_nuc, const double* dm0,
+                          double* mo_coeff, double* mo_energy, double* mo_occ, double* dm, double* vhf_out,
+                          double* trace, nbd_scf_result* result) {
+  return guarded(c, [&] {
+    c->timers.reset();
+    NBD_REQUIRE(c->scf_ready && c->projector == NBD_MU_SHIFT, NBD_ERR_STATE, "nbd_scf_setup(projector = NBD_MU_SHIFT) first");
+    NBD_REQUIRE(dm0 && max_cycle >= 1, NBD_ERR_ARG, "dm0 is required (PySCF's minao guess needs basis data)");
+    const int n = c->nao, ns = c->nspin;
+    const long nn = (long)n * n;
+    const double conv_tol_grad = std::sqrt(conv_tol);
+    c->Ssave.ensure(nn);
+    {
+    StageScope ts_all(c->timers, c->stream, "scf_total");
+    // dm = dm0 ; vhf = get_veff(dm) ; e_tot           (pyscf/scf/hf.py:kernel prologue)
+    h2d(c, c->D.p, dm0, (size_t)ns * nn);
+    {
+      double* tmp = c->dm0f.ensure((size_t)ns * nn);
+      NBD_CUDA(cudaMemcpyAsync(tmp, c->D.p, sizeof(double) * nn * ns, cudaMemcpyDeviceToDevice, c->stream));
+      std::vector<int> jb;
+      std::vector<KGroup> groups;
+      const int Ntot = factor_densities(c, tmp, ns, jb, groups);
+      scf_build_fock(c, Ntot, groups);
+    }
+    double e_tot = mu_energy(c, e_nuc);
+    // CDIIS with Corth from eig(F0, S)
+    c->diis.init(8, ns * nn, true);
+    mu_eig(c, c->F.p, c->Corth.p);
+    double* err = c->FG.p;
+    int conv = 0, cycles = 0;
+    double norm_g = 0.0, norm_dd = 0.0;
+    int tr = 0;
+    auto new_density = [&]() {  // eig -> occ -> dm -> vhf -> e_tot -> F = h + vhf
+      mu_eig(c, c->F.p, c->Ct.p);
+      scf_make_density(c);
+      const int Ntot = scf_stage_occupied(c);
+      scf_build_fock(c, Ntot, scf_occ_groups(c));
+    };
+    auto scalars = [&](double& e_new) {
+      e_new = mu_energy(c, e_nuc);
+      norm_g = mu_grad_norm(c);
+      double t[8];
+      scf_traces(c, nullptr, nullptr, nullptr, true, t);
+      double dd = 0.0;
+      for (int s = 0; s < ns; ++s) dd += t[4 * s + 3];
+      norm_dd = std::sqrt(dd);
+      if (trace) {
+        trace[3 * tr + 0] = e_new;
+        trace[3 * tr + 1] = norm_g;
+        trace[3 * tr + 2] = norm_dd;
+      }
+      ++tr;
+    };
+    for (int cycle = 0; cycle < max_cycle; ++cycle) {
+      StageScope ts(c->timers, c->stream, "iter_total");
+      const double last_e = e_tot;
+      if (cycle >= 1) {  // get_fock(..., cycle, diis): CDIIS from cycle 1
+        mu_cdiis_errvec(c, err);
+        diis_update(c, c->diis, c->F.p, err);
+      }
+      new_density();
+      scalars(e_tot);
+      ++cycles;
+      if (std::fabs(e_tot - last_e) < conv_tol && norm_g < conv_tol_grad) {
+        conv = 1;
+        break;
+      }
+    }
+    if (conv) {  // extra cycle (conv_check)
+      const double last_e = e_tot;
+      new_density();
+      scalars(e_tot);
+      conv = (std::fabs(e_tot - last_e) < conv_tol * 10 || norm_g < conv_tol_grad * 3) ? 1 : 0;
+    }
+    check_devinfo(c, 1, "generalised eigensolve");
+    scf_export(c, mo_coeff, mo_energy, dm, vhf_out, c->vhf.p);
+    if (mo_occ)
+      for (int s = 0; s < ns; ++s)
+        for (int i = 0; i < n; ++i) mo_occ[(long)s * n + i] = i < scf_nocc(c, s) ? scf_occ(c) : 0.0;
+    if (result) {
+      result->converged = conv;
+      result->cycles = cycles;
+      result->e_tot = e_tot;
+      result->energy[0] = result->energy[1] = 0.0;
+      result->norm_ddm = norm_dd;
+      result->norm_grad = norm_g;
+    }
+    }
+    finish_call(c);
+  });
+}

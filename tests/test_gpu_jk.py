@@ -1,0 +1,98 @@
+"""GPU parity: 3-centre tensor layout and the density-fitted J/K build against the CPU oracle."""
+import numpy as np
+import pytest
+
+from nbed_b200 import synthetic as syn
+from oracle import pyscf_restatement as ps
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(7, 21, (4, 4)), (24, 72, (5, 4)), (33, 50, (3, 0)), (45, 64, (9, 11)), (174, 96, (9, 9)), (100, 40, (17, 20))]
+
+
+def _cderi(n, naux, seed=3):
+    return syn.synth_cderi_rows(seed, n, 0.7 / np.sqrt(n * naux) * 3, np.arange(naux))
+
+
+@pytest.mark.parametrize("n,naux", [(7, 21), (24, 72), (33, 5), (64, 3), (65, 9), (174, 40)])
+def test_cderi_roundtrip_bit_exact(ctx, n, naux):
+    rng = np.random.default_rng(n)
+    b = rng.normal(size=(naux, n * (n + 1) // 2))
+    ctx.load_cderi(b)
+    back = ctx.cderi_download(0, naux)
+    assert np.array_equal(back, b)
+    part = ctx.cderi_download(naux // 2, naux - naux // 2)
+    assert np.array_equal(part, b[naux // 2 :])
+
+
+@pytest.mark.parametrize("n,naux", [(7, 21), (45, 17), (174, 12)])
+def test_cderi_synth_bit_exact(ctx, n, naux):
+    ctx.cderi_alloc(n, naux)
+    ctx.cderi_synth(5, 0.125, 11)
+    want = syn.synth_cderi_rows(5, n, 0.125, np.arange(11, 11 + naux))
+    assert np.array_equal(ctx.cderi_download(0, naux), want)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,naux,nocc", SIZES)
+def test_jk_occupied_orbitals(ctx, n, naux, nocc, variant):
+    rng = np.random.default_rng(n + naux)
+    b = _cderi(n, naux)
+    ctx.load_cderi(b)
+    ctx.set_option("jk_variant", variant)
+    ctx.set_option("gemm_variant", variant)
+    try:
+        orbs = [rng.normal(size=(n, o)) / np.sqrt(n) for o in nocc]
+        vj, vk = ctx.jk_orbitals(orbs)
+    finally:
+        ctx.set_option("jk_variant", 0)
+        ctx.set_option("gemm_variant", 0)
+    rj, rk = ps.df_get_jk_occ(b, orbs)
+    scale = max(1.0, np.abs(rj).max(), np.abs(rk).max())
+    assert np.abs(vj - rj).max() <= 1e-12 * scale
+    assert np.abs(vk - rk).max() <= 1e-12 * scale
+    assert np.array_equal(vj, vj.transpose(0, 2, 1))
+    assert np.array_equal(vk, vk.transpose(0, 2, 1))
+
+
+def test_jk_aux_chunking(ctx):
+    n, naux, nocc = 45, 64, (9, 11)
+    rng = np.random.default_rng(1)
+    b = _cderi(n, naux)
+    ctx.load_cderi(b)
+    orbs = [rng.normal(size=(n, o)) / np.sqrt(n) for o in nocc]
+    vj0, vk0 = ctx.jk_orbitals(orbs)
+    ctx.set_option("x_budget_mb", 0)  # one aux row per chunk
+    try:
+        vj1, vk1 = ctx.jk_orbitals(orbs)
+    finally:
+        ctx.set_option("x_budget_mb", 3072)
+    assert np.abs(vj0 - vj1).max() < 1e-13
+    assert np.abs(vk0 - vk1).max() < 1e-13
+
+
+@pytest.mark.parametrize("n,naux", [(7, 21), (45, 30), (100, 16)])
+def test_jk_dense_density(ctx, n, naux):
+    rng = np.random.default_rng(n)
+    b = _cderi(n, naux)
+    ctx.load_cderi(b)
+    a = rng.normal(size=(2, n, n)) / n
+    dm = a + a.transpose(0, 2, 1)  # indefinite symmetric "densities"
+    vj, vk = ctx.jk_dm(dm)
+    rj, rk = ps.df_get_jk(b, dm)
+    scale = max(1.0, np.abs(rj).max(), np.abs(rk).max())
+    assert np.abs(vj - rj).max() <= 1e-11 * scale
+    assert np.abs(vk - rk).max() <= 1e-11 * scale
+
+
+def test_jk_empty_inputs(ctx):
+    n = 12
+    ctx.cderi_alloc(n, 0)  # rank with an empty aux shard
+    vj, vk = ctx.jk_orbitals([np.ones((n, 2)) / n, np.ones((n, 1))])
+    assert not vj.any() and not vk.any()
+    b = _cderi(n, 8)
+    ctx.load_cderi(b)
+    vj, vk = ctx.jk_orbitals([np.zeros((n, 0)), np.ones((n, 1)) / n])
+    rj, rk = ps.df_get_jk_occ(b, [np.zeros((n, 0)), np.ones((n, 1)) / n])
+    assert np.abs(vj - rj).max() < 1e-13 and np.abs(vk - rk).max() < 1e-13
+    assert not vk[0].any() and not vj[0].any()
