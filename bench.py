@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the Nbed hot path on B200: embedded-SCF iterations/s (+ ao2mo GB/s), roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU algorithm on the host cores
+
+Workload (BASELINE.json configs[3]): synthetic (H2O)32 / def2-TZVP-shaped Huzinaga embedded SCF, n = 1376 AOs,
+naux = 4128, 5 active occupied orbitals per spin, UHF.  A "step" is one full iteration of the loop of
+nbed/scf/huzinaga_scf.py:154-201 (J/K, Fock + projector, DIIS, orthogonalise, eigensolve, density, energy,
+convergence scalars) on device-resident state.  The 3-centre tensor (32 GB) is far larger than L2, so every
+iteration streams it from HBM; it is sharded by auxiliary index over the ranks (strong scaling: total work is
+fixed) with one NCCL all-reduce of [J, K_a, K_b] per iteration.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from nbed_b200 import synthetic as syn  # noqa: E402
+
+WORKLOADS = {
+    # name: (config key, description)
+    "C4": ("C4_h2o32_def2tzvp", "synthetic (H2O)32/def2-TZVP-shaped Huzinaga embedded SCF (n=1376, naux=4128, o=5/spin, UHF)"),
+    "C5": ("C5_h2o16_def2tzvp", "synthetic (H2O)16/def2-TZVP-shaped (n=688, naux=2064, o=5/spin, UHF)"),
+    "C3": ("C3_ethanol_ccpvtz", "synthetic ethanol/cc-pVTZ-shaped (n=174, naux=522, o=9/spin, UHF)"),
+}
+
+
+_T0 = time.perf_counter()
+
+
+def log(msg: str):
+    """Progress on stderr (stdout carries the single JSON line)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json copy bandwidth)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+FP64_PEAK_TFLOPS = 37.2  # profiles/microbench_r01.md: DMMA m8n8k4 measured on this pool's B200 (= nominal)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def build_problem(key: str):
+    cfg = dict(syn.CONFIGS[key])
+    p = syn.make_problem(seed=1, **cfg)
+    return cfg, p
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle restatement; PySCF is not installable here) on host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_iterations_per_s(key: str, steps: int, naux_sample: int):
+    """Times the oracle's Huzinaga loop on a bounded sample of the aux index and extrapolates J/K linearly in naux.
+
+    Only this function (and --impl reference, which calls it) executes anything under oracle/."""
+    from oracle import nbed_restatement as nr
+    from oracle import pyscf_restatement as ps
+
+    cfg, p = build_problem(key)
+    naux = cfg["naux"]
+    naux_sample = min(naux_sample, naux)
+    b = p.cderi_rows(np.arange(naux_sample))
+    mf = ps.DFUHF(p.ovlp, p.hcore, b, p.nelec, max_cycle=steps, conv_tol=0.0)
+    stamps, jk = [], [0.0]
+    inner = mf.get_veff
+
+    def timed_veff(*a, **k):
+        t = time.perf_counter()
+        stamps.append(t)
+        out = inner(*a, **k)
+        jk[0] += time.perf_counter() - t
+        return out
+
+    mf.get_veff = timed_veff
+    nr.huzinaga_scf(mf, p.v_emb, p.dm_enviro, dm_conv_tol=0.0)
+    t_end = time.perf_counter()
+    cycles = len(stamps)
+    t_loop = t_end - stamps[0]
+    t_jk = jk[0] / cycles
+    t_rest = t_loop / cycles - t_jk
+    t_full = t_jk * (naux / naux_sample) + t_rest
+    return {
+        "iters_per_s": 1.0 / t_full,
+        "t_jk_sample_s": t_jk,
+        "t_rest_s": t_rest,
+        "cycles": cycles,
+        "sample": f"{cycles} iterations of the oracle loop at n={cfg['n']} on {naux_sample} of {naux} aux rows; "
+                  f"J/K time scaled x{naux / naux_sample:.1f}, the n^3 stages measured in full",
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    key, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    r = cpu_iterations_per_s(key, max(1, args.steps + args.warmup), args.cpu_sample_rows)
+    wall = time.perf_counter() - t0
+    line = {
+        "impl": "reference",
+        "metric": "embedded_scf_iterations_per_s", "value": r["iters_per_s"], "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["iters_per_s"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "note": "PySCF is not installed on this image: the CPU arm is the NumPy/OpenBLAS "
+                   "restatement of the reference algorithm (oracle/), density-fitted like the GPU arm"},
+        "cpu_baseline": {"value": r["iters_per_s"], "unit": "iterations/s", "cores": cores, "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["iters_per_s"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from nbed_b200.backend import B200Context, NBD_HUZINAGA
+
+    key, desc = WORKLOADS[args.workload]
+    cfg, p = build_problem(key)
+    n, naux = cfg["n"], cfg["naux"]
+    ctx = B200Context(local)
+    if world > 1:
+        ctx.comm_init_from_torch()
+    # contiguous aux shard of this rank
+    lo = naux * rank // world
+    hi = naux * (rank + 1) // world
+    ctx.cderi_alloc(n, hi - lo)
+    ctx.cderi_synth(p.seed, p.scale, lo)  # stated boundary: integrals are generated once, outside the timed loop
+    log(f"3-centre tensor shard [{lo}, {hi}) of {naux} rows resident ({8e-9 * (hi - lo) * n * (n + 1) / 2:.1f} GB packed)")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx.scf_setup(p.nelec, p.ovlp, p.hcore, p.v_emb, p.dm_enviro, NBD_HUZINAGA)
+    ctx.scf_bench_init()
+    log("static set-up and initial guess done")
+    it = 0
+    for _ in range(args.warmup):
+        ctx.scf_bench_iteration(it)
+        log(f"warm-up iteration {it}: {ctx.timer_ms('iter_total'):.2f} ms {ctx.timers()}")
+        it += 1
+    stage_keys = ("jk_x", "jk_rho", "jk_k", "jk_j", "jk_total", "allreduce", "fock", "diis", "orth", "eigh", "density",
+                  "energy", "iter_total")
+    stages = {k: 0.0 for k in stage_keys}
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    launches0 = ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e, nd = ctx.scf_bench_iteration(it)  # returns after the iteration's scalars are back on the host
+        it += 1
+        for k in stage_keys:
+            stages[k] += ctx.timer_ms(k)
+    barrier()
+    t1 = time.perf_counter()
+    launches = ctx.launch_count - launches0
+    log(f"timed {args.steps} iterations in {(t1 - t0) * 1e3:.1f} ms")
+    clocks = sampler.stop(t0, t1) if sampler else None
+    # device time of the K iterations (CUDA events on the library's stream), max over ranks
+    dev_ms = max_over_ranks(stages["iter_total"])
+    wall_ms = max_over_ranks((t1 - t0) * 1e3)
+    ms_per_step = dev_ms / args.steps
+    for k in stages:
+        stages[k] /= args.steps
+    if not np.all(np.isfinite(e)):
+        raise RuntimeError(f"non-finite SCF energies in the benchmark loop: {e}")
+
+    # ---- roofline of the dominant kernel (J/K pass 1: symmetric panel half-transform) -------------------
+    hbm_gbs, peak_src = measured_peaks()
+    naux_loc = hi - lo
+    ntot = 2 * cfg["nocc"]
+    packed_bytes = 8.0 * naux_loc * n * (n + 1) / 2
+    x_bytes = 8.0 * naux_loc * ntot * n
+    kern = {
+        "jk_x": {"bytes": packed_bytes + x_bytes, "flops": 4.0 * naux_loc * n * n * ntot / 2 * 1.0},
+        "jk_j": {"bytes": packed_bytes + 8.0 * n * n, "flops": 2.0 * naux_loc * n * n / 2},
+        "jk_k": {"bytes": x_bytes + 16.0 * n * n, "flops": 2.0 * naux_loc * ntot * n * n / 2},
+    }
+    # jk_x flops: X = B C is 2 n^2 per (P, column); symmetric storage does not reduce the multiply count
+    kern["jk_x"]["flops"] = 2.0 * naux_loc * n * n * ntot
+    dom = max(("jk_x", "jk_j", "jk_k"), key=lambda k: stages[k])
+    t_dom = stages[dom] * 1e-3
+    ach_gbs = kern[dom]["bytes"] / t_dom / 1e9
+    ach_tf = kern[dom]["flops"] / t_dom / 1e12
+    frac_hbm, frac_tensor = ach_gbs / hbm_gbs, ach_tf / FP64_PEAK_TFLOPS
+    if frac_hbm >= frac_tensor:
+        roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": frac_hbm}
+    else:
+        roof = {"bound": "tensor", "achieved": ach_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": frac_tensor}
+    roof.update({"kernel": {"jk_x": "symm_panel_kernel", "jk_j": "j_pass_kernel", "jk_k": "gemm_dmma_kernel (K Gram)"}[dom],
+                 "traffic": None, "ms_per_launch": stages[dom], "peak_source": peak_src,
+                 "other_axis": {"hbm_frac": frac_hbm, "fp64_tensor_frac": frac_tensor,
+                                "fp64_peak_tflops": FP64_PEAK_TFLOPS}})
+    # whole J/K against the two-pass model of SURVEY.md 8(d): max(F/P64, B/BW) / t
+    f_jk = 4.0 * naux_loc * n * n + 2 * 4.0 * naux_loc * n * n * cfg["nocc"]
+    b_jk = 2 * packed_bytes + 3 * 8.0 * n * n
+    t_roof = max(f_jk / (FP64_PEAK_TFLOPS * 1e12), b_jk / (hbm_gbs * 1e9))
+    jk_model = {"t_roof_ms": t_roof * 1e3, "t_measured_ms": stages["jk_total"], "frac": t_roof * 1e3 / stages["jk_total"]}
+
+    line = {
+        "metric": "embedded_scf_iterations_per_s", "value": 1e3 / ms_per_step, "unit": "iterations/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "n": n, "naux": naux, "nocc_per_spin": cfg["nocc"], "n_env": cfg["n_env"],
+                   "sharding": f"aux-index x{world}", "l2": "3-centre tensor (>= 4 GB per rank) exceeds the 126 MB L2: "
+                   "every iteration streams it from HBM", "eigensolver": "cuSOLVER dsyevd, included in value; "
+                   "also reported separately"},
+        "wall_ms_per_step": wall_ms / args.steps,
+        "stages_ms": stages,
+        "iters_per_s_excl_eigh": 1e3 / max(1e-9, ms_per_step - stages["eigh"]),
+        "jk_only_per_s": 1e3 / stages["jk_total"],
+        "jk_two_pass_model": jk_model,
+        "roofline": roof,
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+
+    # ---- extras on rank 0 at N = 1: end-to-end through the host API, ao2mo GB/s, CPU baseline -------------
+    if world == 1 and not args.no_extras:
+        from nbed_b200.scf import B200UHF, huzinaga_scf
+
+        mf = B200UHF(ctx, p.ovlp, p.hcore, p.nelec, max_cycle=args.steps, conv_tol=0.0)
+        huzinaga_scf(mf, p.v_emb, p.dm_enviro, dm_conv_tol=0.0)  # warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = huzinaga_scf(mf, p.v_emb, p.dm_enviro, dm_conv_tol=0.0)
+        t_e2e = time.perf_counter() - t0
+        nn8 = 8 * n * n
+        line["e2e"] = {"value": args.steps / t_e2e, "unit": "iterations/s",
+                       "h2d_bytes_per_step": (2 + 2 + 2) * nn8 / args.steps,
+                       "d2h_bytes_per_step": (2 * 3 * nn8 + 2 * 8 * n) / args.steps + 8 * 8,
+                       "what": "nbed_b200.scf.huzinaga_scf(scf_method, v_emb, dm_env) with host NumPy inputs/outputs, "
+                               f"{args.steps} cycles per call (S, h, V, gamma H2D; per-cycle scalars D2H; C, eps, D, Huz D2H)"}
+        del out
+        log(f"e2e host-API run: {t_e2e * 1e3:.1f} ms for {args.steps} cycles")
+        # ao2mo at the C5 shape (BASELINE configs[4]): m = 40 per spin
+        c5, p5 = build_problem("C5_h2o16_def2tzvp")
+        ctx.cderi_alloc(c5["n"], c5["naux"])
+        ctx.cderi_synth(p5.seed, p5.scale, 0)
+        mo = syn.random_orthonormal_mos(p5.ovlp, c5["m"], 0)
+        ctx.ao2mo(mo[0], mo[1])
+        ao_ms = []
+        for _ in range(3):
+            ctx.ao2mo(mo[0], mo[1])
+            ao_ms.append(ctx.timer_ms("ao2mo_total"))
+        ao_t = min(ao_ms) * 1e-3
+        log(f"ao2mo: {ao_ms} ms")
+        m = c5["m"]
+        b_ao = 8.0 * c5["naux"] * c5["n"] * (c5["n"] + 1) / 2 + 4 * 8.0 * m**4
+        f_ao = 2 * (2.0 * c5["naux"] * c5["n"] ** 2 * m + 2.0 * c5["naux"] * c5["n"] * m * m) + 3 * 2.0 * c5["naux"] * m**4
+        line["ao2mo"] = {"workload": f"(H2O)16-shaped n={c5['n']} naux={c5['naux']} m={m} UHF", "ms": ao_t * 1e3,
+                         "gbs": b_ao / ao_t / 1e9, "tflops": f_ao / ao_t / 1e12,
+                         "fp64_tensor_frac": f_ao / ao_t / 1e12 / FP64_PEAK_TFLOPS,
+                         "stages_ms": {k: ctx.timer_ms(k) for k in ("ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm")}}
+        if not args.no_cpu:
+            r = cpu_iterations_per_s(key, 3, args.cpu_sample_rows)
+            line["cpu_baseline"] = {"value": r["iters_per_s"], "unit": "iterations/s", "cores": os.cpu_count() or 1,
+                                    "kind": "port", "sample": r["sample"]}
+    ctx.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-rows", type=int, default=48)
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / ao2mo / cpu_baseline (profiling runs)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 2);
+      mbar_init(&empty[s], XK_CONSUMER_WARPS);
     }
     mbar_fence_init();
   }
@@ -234,24 +234,28 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
       const int I = ij >> 16, J = ij & 0xffff;
       const bool do_row = (I & 7) == warp;
       const bool do_col = ((J & 7) == warp) && (I != J);
-      if (!do_row && !do_col) continue;
       const int st = (int)(q % S);
+      // Every consumer warp waits on, and releases, every tile - also those it has no task on.  A parity wait
+      // only tells the current phase from the previous one, so all waiters must stay within one round of a
+      // stage; gating the refill on all 8 warps guarantees that (and costs two shared-memory ops per tile).
       mbar_wait(&full[st], (uint32_t)((q / S) & 1));
-      const double* tile = stages + (size_t)st * TILE_ELEMS;
-      if (do_row) {
-        const int slot = I >> 3;
+      if (do_row || do_col) {
+        const double* tile = stages + (size_t)st * TILE_ELEMS;
+        if (do_row) {
+          const int slot = I >> 3;
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s)
-          if (slot == s) xk_task_row<NB>(X[s], tile, crow, 32 * J, gq, tq, xoff);
-      }
-      if (do_col) {
-        const int slot = J >> 3;
+          for (int s = 0; s < NSLOT; ++s)
+            if (slot == s) xk_task_row<NB>(X[s], tile, crow, 32 * J, gq, tq, xoff);
+        }
+        if (do_col) {
+          const int slot = J >> 3;
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s)
-          if (slot == s) xk_task_col<NB>(X[s], tile, crow, 32 * I, tq, yoff);
+          for (int s = 0; s < NSLOT; ++s)
+            if (slot == s) xk_task_col<NB>(X[s], tile, crow, 32 * I, tq, yoff);
+        }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[st], (do_row ? 1u : 0u) + (do_col ? 1u : 0u) + (I == J ? 1u : 0u));
+      if (lane == 0) mbar_arrive(&empty[st]);
     }
     // write this warp's panels of X[P] and reset the accumulators
     double* xo = p.X + ((size_t)P * p.Ntot + col0) * p.n_ld;

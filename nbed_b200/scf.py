@@ -1,0 +1,264 @@
+"""Host-side mirror of the reference's embedded-SCF interface, backed by the sm_100a C-ABI.
+
+Mirrors (same names, argument meaning and return contract):
+
+* ``huzinaga_scf``            /root/reference nbed/scf/huzinaga_scf.py:93-206
+* ``get_huzinaga_operator``   nbed/scf/huzinaga_scf.py:65-90   (device GEMM + fused symmetrise)
+* ``energy_elec``             nbed/scf/embedded_hcore_funcs.py:11-46
+* ``mu_embed``                NbedDriver._mu_embed, nbed/driver.py:500-538 (+ ``_env_projector`` :433-449)
+* ``B200RHF`` / ``B200UHF``   the duck-typed PySCF SCF-object protocol the reference drives:
+  ``get_ovlp, get_hcore, get_veff, get_jk, get_j, get_occ, make_rdm1, energy_elec, energy_tot, energy_nuc,
+  get_fock, max_cycle, conv_tol, mo_coeff, mo_occ, mo_energy, e_tot, converged, mol``.
+
+All arithmetic runs on the GPU through ``nbed_b200.backend.B200Context``; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import copy as _copy
+
+import numpy as np
+
+from .backend import NBD_HUZINAGA, NBD_MU_SHIFT, B200Context
+
+
+class TaggedArray(np.ndarray):
+    """ndarray carrying ``mo_coeff`` / ``mo_occ`` like ``pyscf.lib.tag_array`` (lets K use occupied orbitals)."""
+
+
+def tag_array(a, **kw):
+    t = np.asarray(a).view(TaggedArray)
+    for k, v in kw.items():
+        setattr(t, k, v)
+    return t
+
+
+class _Mol:
+    """The few ``mol`` attributes the reference reads or overwrites (nbed/driver.py:262-287)."""
+
+    def __init__(self, nelec, e_nuc=0.0):
+        self.nelec = tuple(int(x) for x in nelec)
+        self.nelectron = int(sum(self.nelec))
+        self.spin = self.nelec[0] - self.nelec[1]
+        self._e_nuc = float(e_nuc)
+
+    def energy_nuc(self):
+        return self._e_nuc
+
+
+class _B200SCF:
+    """Density-fitted SCF object over a device-resident 3-centre tensor (``mf.density_fit()`` analogue)."""
+
+    unrestricted = True
+
+    def __init__(self, ctx: B200Context, ovlp, hcore, nelec, e_nuc=0.0, max_cycle=50, conv_tol=1e-9, mol=None):
+        self.ctx = ctx
+        self._s = np.ascontiguousarray(ovlp, dtype=np.float64)
+        self._h = np.ascontiguousarray(hcore, dtype=np.float64)
+        self.mol = mol if mol is not None else _Mol(nelec, e_nuc)
+        self.max_cycle = max_cycle
+        self.conv_tol = conv_tol
+        self.verbose = 1
+        self.max_memory = 4000
+        self.mo_coeff = self.mo_occ = self.mo_energy = None
+        self.e_tot = None
+        self.converged = False
+        self.scf_summary = {}
+        if ctx.nao != self._s.shape[0]:
+            raise ValueError(f"context holds a {ctx.nao}-AO 3-centre tensor, overlap is {self._s.shape}")
+
+    # -- protocol ---------------------------------------------------------------------------------
+    @property
+    def nelec(self):
+        return self.mol.nelec
+
+    def copy(self):
+        new = _copy.copy(self)
+        new.scf_summary = dict(self.scf_summary)
+        return new
+
+    def get_ovlp(self, *a):
+        return self._s
+
+    def get_hcore(self, *a):
+        return self._h
+
+    def energy_nuc(self):
+        return self.mol.energy_nuc()
+
+    def get_jk(self, mol=None, dm=None, hermi=1, with_j=True, with_k=True, omega=None):
+        """pyscf.df.df_jk.get_jk: occupied-orbital route when ``dm`` carries ``mo_coeff``/``mo_occ`` tags."""
+        if dm is None:
+            dm = self.make_rdm1()
+        arr = np.asarray(dm)
+        shape = arr.shape
+        n = shape[-1]
+        mo_coeff = getattr(dm, "mo_coeff", None)
+        if mo_coeff is not None:
+            mo_occ = np.asarray(dm.mo_occ)
+            mo_coeff = np.asarray(mo_coeff).reshape(-1, n, mo_occ.shape[-1])
+            mo_occ = mo_occ.reshape(-1, mo_occ.shape[-1])
+            orbs = [mo_coeff[k][:, mo_occ[k] > 0] * np.sqrt(mo_occ[k][mo_occ[k] > 0]) for k in range(mo_coeff.shape[0])]
+            vj, vk = self.ctx.jk_orbitals(orbs, with_j=with_j, with_k=with_k)
+        else:
+            vj, vk = self.ctx.jk_dm(arr.reshape(-1, n, n), with_j=with_j, with_k=with_k)
+        return (vj.reshape(shape) if with_j else None), (vk.reshape(shape) if with_k else None)
+
+    def get_j(self, mol=None, dm=None, hermi=1, omega=None):
+        return self.get_jk(mol, dm, hermi, with_k=False)[0]
+
+    def get_k(self, mol=None, dm=None, hermi=1, omega=None):
+        return self.get_jk(mol, dm, hermi, with_j=False)[1]
+
+    def make_rdm1(self, mo_coeff=None, mo_occ=None):
+        mo_coeff = self.mo_coeff if mo_coeff is None else mo_coeff
+        mo_occ = self.mo_occ if mo_occ is None else mo_occ
+        mo_coeff, mo_occ = np.asarray(mo_coeff), np.asarray(mo_occ)
+        if mo_coeff.ndim == 2:
+            sel = mo_occ > 0
+            dm = (mo_coeff[:, sel] * mo_occ[sel]) @ mo_coeff[:, sel].T
+        else:
+            dm = np.array([(mo_coeff[s][:, mo_occ[s] > 0] * mo_occ[s][mo_occ[s] > 0]) @ mo_coeff[s][:, mo_occ[s] > 0].T
+                           for s in range(mo_coeff.shape[0])])
+        return tag_array(dm, mo_coeff=mo_coeff, mo_occ=mo_occ)
+
+    def energy_tot(self, dm=None, h1e=None, vhf=None):
+        return self.energy_elec(dm, h1e, vhf)[0] + self.energy_nuc()
+
+    def get_fock(self, h1e=None, s1e=None, vhf=None, dm=None, cycle=-1, diis=None, diis_start_cycle=1):
+        if h1e is None:
+            h1e = self.get_hcore()
+        if vhf is None:
+            vhf = self.get_veff(dm=dm)
+        return np.asarray(h1e) + vhf
+
+
+class B200UHF(_B200SCF):
+    unrestricted = True
+
+    def get_veff(self, mol=None, dm=None, dm_last=0, vhf_last=0, hermi=1):
+        if dm is None:
+            dm = self.make_rdm1()
+        if isinstance(dm, np.ndarray) and dm.ndim == 2:
+            dm = np.asarray((dm * 0.5, dm * 0.5))
+        vj, vk = self.get_jk(mol, dm, hermi)
+        return vj[0] + vj[1] - vk
+
+    def get_occ(self, mo_energy=None, mo_coeff=None):
+        mo_energy = np.asarray(self.mo_energy if mo_energy is None else mo_energy)
+        occ = np.zeros_like(mo_energy)
+        for s in range(2):
+            occ[s, np.argsort(mo_energy[s], kind="stable")[: self.nelec[s]]] = 1
+        return occ
+
+    def energy_elec(self, dm=None, h1e=None, vhf=None):
+        return energy_elec(self, dm, h1e, vhf)
+
+
+class B200RHF(_B200SCF):
+    unrestricted = False
+
+    def get_veff(self, mol=None, dm=None, dm_last=0, vhf_last=0, hermi=1):
+        if dm is None:
+            dm = self.make_rdm1()
+        vj, vk = self.get_jk(mol, dm, hermi)
+        return vj - vk * 0.5
+
+    def get_occ(self, mo_energy=None, mo_coeff=None):
+        mo_energy = np.asarray(self.mo_energy if mo_energy is None else mo_energy)
+        occ = np.zeros_like(mo_energy)
+        occ[np.argsort(mo_energy, kind="stable")[: self.mol.nelectron // 2]] = 2
+        return occ
+
+    def energy_elec(self, dm=None, h1e=None, vhf=None):
+        if dm is None:
+            dm = self.make_rdm1()
+        if h1e is None:
+            h1e = self.get_hcore()
+        if vhf is None:
+            vhf = self.get_veff(dm=dm)
+        e1 = np.einsum("ij,ji->", h1e, dm)
+        e_coul = 0.5 * np.einsum("ij,ji->", vhf, dm)
+        self.scf_summary["e1"], self.scf_summary["e2"] = e1, e_coul
+        return e1 + e_coul, e_coul
+
+
+# ---- nbed/scf/embedded_hcore_funcs.py:11-46 -----------------------------------------------------------
+def energy_elec(mf, dm=None, h1e=None, vhf=None):
+    """Electronic energy with a spin-resolved (2, n, n) core Hamiltonian (patched onto the SCF object)."""
+    if dm is None:
+        dm = mf.make_rdm1()
+    if h1e is None:
+        h1e = mf.get_hcore()
+    if isinstance(dm, np.ndarray) and dm.ndim == 2:
+        dm = np.array((dm * 0.5, dm * 0.5))
+    if vhf is None:
+        vhf = mf.get_veff(mf.mol, dm)
+    h1e = np.asarray(h1e)
+    if h1e.ndim == 2:
+        h1e = (h1e, h1e)
+    e1 = np.einsum("ij,ji->", h1e[0], dm[0]) + np.einsum("ij,ji->", h1e[1], dm[1])
+    e_coul = (np.einsum("ij,ji->", vhf[0], dm[0]) + np.einsum("ij,ji->", vhf[1], dm[1])) * 0.5
+    mf.scf_summary["e1"] = float(np.real(e1))
+    mf.scf_summary["e2"] = float(np.real(e_coul))
+    return float(np.real(e1 + e_coul)), float(np.real(e_coul))
+
+
+# ---- nbed/scf/huzinaga_scf.py:93-206 --------------------------------------------------------------------
+def huzinaga_scf(scf_method, embedding_potential, dm_environment_occupied, dm_environment_virtual=None,
+                 dm_conv_tol: float = 1e-6, dm_initial_guess=None, use_DIIS: bool = True, return_info: bool = False):
+    """Huzinaga-projected SCF on the GPU.  Same arguments and return value as the reference function:
+    ``(mo_coeff_std, mo_energy, density_matrix, huzinaga_op_std, conv_flag)``.
+
+    The whole loop (J/K, Fock, projector, DIIS, orthogonalisation, eigensolve, density, energies, convergence) runs
+    device-resident inside one C-ABI call.  ``dm_environment_virtual`` (the PAO virtual projector) is unreachable
+    from the reference driver (nbed/driver.py:819-820 raises) and is rejected here.
+    """
+    if not isinstance(scf_method, _B200SCF):
+        raise TypeError("huzinaga_scf needs a B200RHF / B200UHF SCF object (no CPU fallback)")  # cf. :187
+    if dm_environment_virtual is not None and np.any(np.asarray(dm_environment_virtual)):
+        raise NotImplementedError("virtual-orbital Huzinaga projector (PAO) is not on the supported path")
+    v = np.asarray(embedding_potential, dtype=np.float64)
+    g = np.asarray(dm_environment_occupied, dtype=np.float64)
+    if v.ndim != g.ndim or v.ndim != (3 if scf_method.unrestricted else 2):
+        raise ValueError("embedding_potential / dm_environment_occupied rank does not match the SCF object")
+    ctx = scf_method.ctx
+    ctx.scf_setup(scf_method.nelec, scf_method.get_ovlp(), scf_method.get_hcore(), v, g, NBD_HUZINAGA)
+    c, e, dm, huz, info = ctx.huzinaga_scf(scf_method.max_cycle, scf_method.conv_tol, dm_conv_tol, use_DIIS,
+                                           dm0=dm_initial_guess)
+    occ = scf_method.get_occ(e, c)
+    dm = tag_array(dm, mo_coeff=c, mo_occ=occ)
+    if return_info:
+        return c, e, dm, huz, info["converged"], info
+    return c, e, dm, huz, info["converged"]
+
+
+def get_huzinaga_operator(fock, dm_occ_S, dm_virt_S=None):
+    """-(F gS + (F gS)^T) per spin (rank 3) or -1/2(...) (rank 2): NumPy form for host-side checks."""
+    fds = np.einsum("...ij,...jk->...ik", fock, dm_occ_S)
+    out = fds + np.swapaxes(fds, -1, -2)
+    return out * (-0.5 if fds.ndim == 2 else -1.0)
+
+
+# ---- nbed/driver.py:433-449, 500-538 ----------------------------------------------------------------------
+def mu_embed(localized_scf, embedding_potential, dm_enviro, mu_level_shift: float = 1e6, dm0=None, return_info=False):
+    """Mu-shift embedding: ``v_emb = mu * S gamma S + V``; the SCF (pyscf kernel semantics, CDIIS, dsygvd) runs on
+    the GPU.  Returns ``(localized_scf, v_emb)`` with the SCF object updated like ``kernel()`` would."""
+    if not isinstance(localized_scf, _B200SCF):
+        raise TypeError("mu_embed needs a B200RHF / B200UHF SCF object (no CPU fallback)")
+    if dm0 is None:
+        raise ValueError("dm0 is required: PySCF's 'minao' guess needs atomic basis data that is outside the hot path")
+    s = localized_scf.get_ovlp()
+    g = np.asarray(dm_enviro, dtype=np.float64)
+    v = np.asarray(embedding_potential, dtype=np.float64)
+    ctx = localized_scf.ctx
+    hcore_std = localized_scf.get_hcore()
+    ctx.scf_setup(localized_scf.nelec, s, hcore_std, v, g, NBD_MU_SHIFT, mu_level_shift)
+    c, e, occ, dm, vhf, info = ctx.mu_scf(localized_scf.max_cycle, localized_scf.conv_tol, localized_scf.energy_nuc(), dm0)
+    proj = np.einsum("ij,...jk,kl->...il", s, g, s)
+    v_emb = mu_level_shift * proj + v
+    localized_scf.get_hcore = lambda *args: hcore_std + v_emb  # :529
+    localized_scf.mo_coeff, localized_scf.mo_energy, localized_scf.mo_occ = c, e, occ
+    localized_scf.e_tot, localized_scf.converged = info["e_tot"], info["converged"]
+    if return_info:
+        return localized_scf, v_emb, info
+    return localized_scf, v_emb
