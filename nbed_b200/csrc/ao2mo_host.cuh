@@ -39,16 +39,19 @@ extern "C" int nbd_ao2mo(nbd_ctx* c, int m, const double* ca, const double* cb, 
       const long per_row = (long)Ntot * n_ld * 8;
       const int chunk = (int)std::max<long>(1, std::min<long>(std::max(1, naux), c->x_budget_bytes / per_row));
       double* X = c->d_X.ensure((size_t)chunk * Ntot * n_ld);
+      std::vector<std::pair<int, int>> cols;
+      for (int s = 0; s < nsp; ++s) cols.push_back({s * m, (s + 1) * m});
       for (int p0 = 0; p0 < naux; p0 += chunk) {
         const int np = std::min(chunk, naux - p0);
+        const XLayout XL = make_xlayout(c, np, Ntot, cols);
         {
-          StageScope ts(c->timers, c->stream, "ao2mo_half");  // X[P][p][mu] = sum_nu B[P][mu][nu] C[nu][p]
+          StageScope ts(c->timers, c->stream, "ao2mo_half");  // X_s[(P,p)][mu] = sum_nu B[P][mu][nu] C_s[nu][p]
           half_transform(c, p0, np, c->d_orb.p, Ntot, X);
         }
-        StageScope ts(c->timers, c->stream, "ao2mo_l");  // L[s][P][p][q] = sum_mu X[P][s m + p][mu] C_s[mu][q]
+        StageScope ts(c->timers, c->stream, "ao2mo_l");  // L_s[(P,p)][q] = sum_mu X_s[(P,p)][mu] C_s[mu][q]
         for (int s = 0; s < nsp; ++s)
-          gemm(c, m, m, c->nao, X + (long)s * m * n_ld, n_ld, 1, c->d_orb.p + (long)s * m * n_ld, n_ld, 1,
-               L + ((long)s * naux + p0) * m2, m, 1.0, 0.0, np, (long)Ntot * n_ld, 0, m2);
+          gemm(c, np * m, m, c->nao, X + XL.group_base[s], n_ld, 1, c->d_orb.p + (long)s * m * n_ld, n_ld, 1,
+               L + ((long)s * naux + p0) * m2, m, 1.0, 0.0);
       }
       {
         StageScope ts(c->timers, c->stream, "ao2mo_eri");  // (pq|rs) = sum_P L[P][pq] L'[P][rs]

@@ -1,8 +1,11 @@
 // FP64 tensor-core GEMM used by every GEMM-shaped stage of the hot path (SURVEY.md §2.3 K2 Gram, K4, K6,
-// K7, K8):  C[b] = alpha * A[b] * B[b] + beta * C[b]   with arbitrary element strides, a two-level K
-// addressing (for the [P][i][mu] half-transformed tensor) and an optional lower-triangle-only tile mask.
-// Tiles are staged with cp.async into padded shared memory (conflict-free DMMA fragment loads) through a
-// 4-stage ring; accumulators live in registers (tcgen05/TMEM have no f64 kind).
+// K7, K8):  C[b] = alpha * A[b] * B[b] + beta * C[b]   with arbitrary element strides (so that transposes
+// and the [P][i][mu] half-transformed tensor need no copies) and an optional lower-triangle-only tile mask.
+//
+// tcgen05 / TMEM have no f64 kind, so the accumulators live in registers and the MMA is the warp-level
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  Operand tiles are staged with cp.async (LDGSTS) through a 4-stage
+// ring of padded shared-memory tiles (conflict-free fragment loads); fragments are double-buffered in
+// registers so that the shared-memory latency of step k+1 hides behind the DMMAs of step k.
 #pragma once
 #include "common.cuh"
 
@@ -11,27 +14,18 @@ namespace nbd {
 struct GemmArgs {
   int M, N, K;
   const double* A;
-  long a_is;        // stride of the row index i of A(i,k)
-  long a_ks;        // stride of k inside one K group
-  int a_kb;         // K group length (k -> (k / a_kb) * a_kos + (k % a_kb) * a_ks); <=0 : single level
-  long a_kos;       // stride between K groups
+  long a_is;  // stride of the row index i of A(i,k)
+  long a_ks;  // stride of k
   const double* B;
-  long b_js;        // stride of the column index j of B(k,j)
+  long b_js;  // stride of the column index j of B(k,j)
   long b_ks;
-  int b_kb;
-  long b_kos;
   double* C;
   long ldc;
   double alpha, beta;
   int batch;
   long strideA, strideB, strideC;
-  int lower_only;   // 1: compute only tiles with tile_col <= tile_row (square tiles)
+  int lower_only;  // 1: compute only tiles with tile_col <= tile_row (square tiles)
 };
-
-__device__ __forceinline__ long koff(int k, long ks, int kb, long kos) {
-  if (kb <= 0) return (long)k * ks;
-  return (long)(k / kb) * kos + (long)(k % kb) * ks;
-}
 
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_STAGES = 4;
@@ -47,6 +41,9 @@ gemm_dmma_kernel(GemmArgs g) {
   constexpr int A_ELEMS = A_MC ? BK * A_LD : BM * A_LD;
   constexpr int B_ELEMS = B_NC ? BK * B_LD : BN * B_LD;
   constexpr int MI = WM / 8, NI = WN / 8;
+  constexpr int A_PER_T = BM * BK / NT, B_PER_T = BN * BK / NT;
+  static_assert(BM * BK % NT == 0 && BN * BK % NT == 0, "tile must divide evenly over the threads");
+  static_assert(NT % BM == 0 || BM % NT == 0, "A_MC mapping");
   extern __shared__ __align__(16) double gsm[];
   double* As = gsm;
   double* Bs = gsm + GEMM_STAGES * A_ELEMS;
@@ -61,6 +58,28 @@ gemm_dmma_kernel(GemmArgs g) {
   const int gq = lane >> 2, tq = lane & 3;
   const int wm = (warp / (BN / WN)) * WM, wn = (warp % (BN / WN)) * WN;
 
+  // ---- per-thread copy plan: element j of this thread is (i_fix + j * i_step, k_fix + j * k_step) ----------
+  // A_MC : e = tid + j NT ; m = e % BM , k = e / BM       !A_MC : k = e % BK , m = e / BK
+  int a_m, a_k, a_mstep, a_kstep, b_n, b_k, b_nstep, b_kstep;
+  if (A_MC) {
+    a_m = tid % BM; a_k = tid / BM; a_mstep = (NT % BM == 0) ? 0 : NT; a_kstep = (NT % BM == 0) ? NT / BM : 0;
+  } else {
+    a_k = tid % BK; a_m = tid / BK; a_mstep = NT / BK; a_kstep = 0;
+  }
+  if (B_NC) {
+    b_n = tid % BN; b_k = tid / BN; b_nstep = (NT % BN == 0) ? 0 : NT; b_kstep = (NT % BN == 0) ? NT / BN : 0;
+  } else {
+    b_k = tid % BK; b_n = tid / BK; b_nstep = NT / BK; b_kstep = 0;
+  }
+  const double* a_src = A + (long)(m0 + a_m) * g.a_is + (long)a_k * g.a_ks;
+  const double* b_src = B + (long)(n0 + b_n) * g.b_js + (long)b_k * g.b_ks;
+  const long a_jstep = (long)a_mstep * g.a_is + (long)a_kstep * g.a_ks;
+  const long b_jstep = (long)b_nstep * g.b_js + (long)b_kstep * g.b_ks;
+  const int a_dst0 = A_MC ? a_k * A_LD + a_m : a_m * A_LD + a_k;
+  const int a_dstep = A_MC ? a_kstep * A_LD + a_mstep : a_mstep * A_LD;
+  const int b_dst0 = B_NC ? b_k * B_LD + b_n : b_n * B_LD + b_k;
+  const int b_dstep = B_NC ? b_kstep * B_LD + b_nstep : b_nstep * B_LD;
+
   double acc[MI][NI][2];
 #pragma unroll
   for (int i = 0; i < MI; ++i)
@@ -73,35 +92,17 @@ gemm_dmma_kernel(GemmArgs g) {
     const int k0 = kt * BK;
     double* as = As + st * A_ELEMS;
     double* bs = Bs + st * B_ELEMS;
-    if (A_MC) {
-      for (int e = tid; e < BM * BK; e += NT) {
-        const int m = e % BM, k = e / BM;
-        const bool ok = (m0 + m < g.M) && (k0 + k < g.K);
-        const double* src = ok ? A + (long)(m0 + m) * g.a_is + koff(k0 + k, g.a_ks, g.a_kb, g.a_kos) : A;
-        cp_async8(as + k * A_LD + m, src, ok);
-      }
-    } else {
-      for (int e = tid; e < BM * BK; e += NT) {
-        const int k = e % BK, m = e / BK;
-        const bool ok = (m0 + m < g.M) && (k0 + k < g.K);
-        const double* src = ok ? A + (long)(m0 + m) * g.a_is + koff(k0 + k, g.a_ks, g.a_kb, g.a_kos) : A;
-        cp_async8(as + m * A_LD + k, src, ok);
-      }
+    const double* ap = a_src + (long)k0 * g.a_ks;
+    const double* bp = b_src + (long)k0 * g.b_ks;
+#pragma unroll
+    for (int j = 0; j < A_PER_T; ++j) {
+      const bool ok = (m0 + a_m + j * a_mstep < g.M) && (k0 + a_k + j * a_kstep < g.K);
+      cp_async8(as + a_dst0 + j * a_dstep, ok ? ap + j * a_jstep : A, ok);
     }
-    if (B_NC) {
-      for (int e = tid; e < BN * BK; e += NT) {
-        const int n = e % BN, k = e / BN;
-        const bool ok = (n0 + n < g.N) && (k0 + k < g.K);
-        const double* src = ok ? B + (long)(n0 + n) * g.b_js + koff(k0 + k, g.b_ks, g.b_kb, g.b_kos) : B;
-        cp_async8(bs + k * B_LD + n, src, ok);
-      }
-    } else {
-      for (int e = tid; e < BN * BK; e += NT) {
-        const int k = e % BK, n = e / BK;
-        const bool ok = (n0 + n < g.N) && (k0 + k < g.K);
-        const double* src = ok ? B + (long)(n0 + n) * g.b_js + koff(k0 + k, g.b_ks, g.b_kb, g.b_kos) : B;
-        cp_async8(bs + n * B_LD + k, src, ok);
-      }
+#pragma unroll
+    for (int j = 0; j < B_PER_T; ++j) {
+      const bool ok = (n0 + b_n + j * b_nstep < g.N) && (k0 + b_k + j * b_kstep < g.K);
+      cp_async8(bs + b_dst0 + j * b_dstep, ok ? bp + j * b_jstep : B, ok);
     }
   };
 
@@ -110,6 +111,15 @@ gemm_dmma_kernel(GemmArgs g) {
     if (s < nk) load_stage(s, s);
     cp_async_commit();
   }
+
+  // fragment offsets inside a stage (k4 added at use)
+  int a_off[MI], b_off[NI];
+#pragma unroll
+  for (int i = 0; i < MI; ++i) a_off[i] = A_MC ? tq * A_LD + wm + 8 * i + gq : (wm + 8 * i + gq) * A_LD + tq;
+#pragma unroll
+  for (int j = 0; j < NI; ++j) b_off[j] = B_NC ? tq * B_LD + wn + 8 * j + gq : (wn + 8 * j + gq) * B_LD + tq;
+  constexpr int A_K4 = A_MC ? 4 * A_LD : 4;
+  constexpr int B_K4 = B_NC ? 4 * B_LD : 4;
 
   for (int kt = 0; kt < nk; ++kt) {
     cp_async_wait<GEMM_STAGES - 2>();
@@ -121,19 +131,24 @@ gemm_dmma_kernel(GemmArgs g) {
     }
     const double* as = As + (kt % GEMM_STAGES) * A_ELEMS;
     const double* bs = Bs + (kt % GEMM_STAGES) * B_ELEMS;
+    double a[2][MI], b[2][NI];
 #pragma unroll
-    for (int k4 = 0; k4 < BK; k4 += 4) {
-      double a[MI], b[NI];
+    for (int i = 0; i < MI; ++i) a[0][i] = as[a_off[i]];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) b[0][j] = bs[b_off[j]];
+#pragma unroll
+    for (int s4 = 0; s4 < BK / 4; ++s4) {
+      const int cur = s4 & 1, nxt = cur ^ 1;
+      if (s4 + 1 < BK / 4) {
+#pragma unroll
+        for (int i = 0; i < MI; ++i) a[nxt][i] = as[a_off[i] + (s4 + 1) * A_K4];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) b[nxt][j] = bs[b_off[j] + (s4 + 1) * B_K4];
+      }
 #pragma unroll
       for (int i = 0; i < MI; ++i)
-        a[i] = A_MC ? as[(k4 + tq) * A_LD + wm + 8 * i + gq] : as[(wm + 8 * i + gq) * A_LD + k4 + tq];
 #pragma unroll
-      for (int j = 0; j < NI; ++j)
-        b[j] = B_NC ? bs[(k4 + tq) * B_LD + wn + 8 * j + gq] : bs[(wn + 8 * j + gq) * B_LD + k4 + tq];
-#pragma unroll
-      for (int i = 0; i < MI; ++i)
-#pragma unroll
-        for (int j = 0; j < NI; ++j) dmma(acc[i][j], a[i], b[j]);
+        for (int j = 0; j < NI; ++j) dmma(acc[i][j], a[cur][i], b[cur][j]);
     }
   }
   cp_async_wait<0>();
@@ -159,7 +174,7 @@ gemm_dmma_kernel(GemmArgs g) {
 }
 
 // Obviously-correct CUDA-core variant (option "gemm_variant" = 1): debugging aid and cross-check.
-__global__ void gemm_simple_kernel(GemmArgs g) {
+__global__ void gemm_simple_kernel(GemmArgs g, int tile) {
   const int bz = blockIdx.z;
   const double* A = g.A + (long)bz * g.strideA;
   const double* B = g.B + (long)bz * g.strideB;
@@ -167,10 +182,9 @@ __global__ void gemm_simple_kernel(GemmArgs g) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = blockIdx.y * blockDim.y + threadIdx.y;
   if (row >= g.M || col >= g.N) return;
-  if (g.lower_only && (col / 128) > (row / 128)) return;
+  if (g.lower_only && (col / tile) > (row / tile)) return;
   double s = 0.0;
-  for (int k = 0; k < g.K; ++k)
-    s += A[(long)row * g.a_is + koff(k, g.a_ks, g.a_kb, g.a_kos)] * B[(long)col * g.b_js + koff(k, g.b_ks, g.b_kb, g.b_kos)];
+  for (int k = 0; k < g.K; ++k) s += A[(long)row * g.a_is + (long)k * g.a_ks] * B[(long)col * g.b_js + (long)k * g.b_ks];
   double* p = C + (long)row * g.ldc + col;
   double v = g.alpha * s;
   if (g.beta != 0.0) v += g.beta * (*p);
@@ -198,21 +212,29 @@ inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g) {
   return cudaGetLastError();
 }
 
-// Dispatch on tile size (large problems: 128x128 tiles; small: 32x32) and on operand contiguity.
-inline cudaError_t launch_gemm(cudaStream_t st, GemmArgs g, int variant, long* launches) {
+// Tile size by problem size: the largest of 128 / 64 / 32 square tiles that still yields about one CTA per SM
+// (148 SMs); operand contiguity picks the shared-memory tile orientation.
+inline cudaError_t launch_gemm(cudaStream_t st, GemmArgs g, int variant, long* launches, int sm_count = 148) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
   if (g.batch <= 0) g.batch = 1;
   if (launches) ++*launches;
+  auto ctas = [&](int t) {
+    const long tm = (g.M + t - 1) / t, tn = (g.N + t - 1) / t;
+    const long per = g.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+    return per * g.batch;
+  };
+  int tile = 128;
+  if (ctas(128) < (long)sm_count * 3 / 4) tile = 64;
+  if (tile == 64 && ctas(64) < (long)sm_count / 2 && g.M <= 256 && g.N <= 256) tile = 32;
   if (variant == 1 || g.K <= 0) {
     dim3 b(32, 8), grid((g.N + 31) / 32, (g.M + 7) / 8, g.batch);
-    gemm_simple_kernel<<<grid, b, 0, st>>>(g);
+    gemm_simple_kernel<<<grid, b, 0, st>>>(g, tile);
     return cudaGetLastError();
   }
   const bool a_mc = (g.a_is == 1);
   const bool b_nc = (g.b_js == 1);
   // lower_only masks whole tiles above the diagonal; every element with col <= row is still produced for
-  // either tile size, which is all the mirror kernel needs.
-  const bool small = (g.M <= 256 && g.N <= 256);
+  // any tile size, which is all the mirror kernel needs.
 #define NBD_GEMM_DISPATCH(BM, BN, WM, WN)                                          \
   do {                                                                             \
     if (a_mc && b_nc) return launch_gemm_cfg<BM, BN, WM, WN, true, true>(st, g);   \
@@ -220,7 +242,8 @@ inline cudaError_t launch_gemm(cudaStream_t st, GemmArgs g, int variant, long* l
     if (!a_mc && b_nc) return launch_gemm_cfg<BM, BN, WM, WN, false, true>(st, g); \
     return launch_gemm_cfg<BM, BN, WM, WN, false, false>(st, g);                   \
   } while (0)
-  if (small) NBD_GEMM_DISPATCH(32, 32, 16, 16);
+  if (tile == 32) NBD_GEMM_DISPATCH(32, 32, 16, 16);
+  if (tile == 64) NBD_GEMM_DISPATCH(64, 64, 32, 32);
   NBD_GEMM_DISPATCH(128, 128, 64, 32);
 #undef NBD_GEMM_DISPATCH
 }

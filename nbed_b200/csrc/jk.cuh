@@ -94,11 +94,13 @@ __global__ void synth_tiled_kernel(double* __restrict__ tiled, const int* __rest
 
 // ---- pass 1: X = B_sym * C, one B tile enters the SM once and is used in both directions -------------
 struct XArgs {
-  const double* Bt;   // [naux][ntiles][1024]
-  const int* seq;     // [ntiles]
-  const double* Ct;   // [Ntot][n_ld]
-  double* X;          // [naux][Ntot][n_ld]
-  int naux, ntiles, nb, n_ld, Ntot, nslices, nstages;
+  const double* Bt;     // [naux][ntiles][1024]
+  const int* seq;       // [ntiles]
+  const double* Ct;     // [Ntot][n_ld]
+  double* X;            // group-major: column i of aux row P lives at X + xbase[i] + P * xstride[i]  (n_ld doubles)
+  const long* xbase;    // [Ntot]
+  const long* xstride;  // [Ntot]
+  int naux, ntiles, nb, n_ld, Ntot, nslices, nstages, ncolmax;
 };
 
 // 8 consumer warps (warpgroups 0-1) + one producer warpgroup.  Registers are re-balanced with setmaxnreg
@@ -158,10 +160,12 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
   const int slice = blockIdx.x % p.nslices;
   const int col0 = slice * NCOL;
   const int ncol = min(NCOL, p.Ntot - col0);
-  double* cts = reinterpret_cast<double*>(xsm + 256);
-  // stage buffers start at the next 128-byte boundary after (ncol + 1) rows of Ct
-  const size_t ct_bytes = ((size_t)(ncol + 1) * ct_ld * 8 + 127) & ~(size_t)127;
-  double* stages = reinterpret_cast<double*>(xsm + 256 + ct_bytes);
+  // layout: [256 B barriers][tile sequence][(ncolmax + 1) rows of Ct][S stage buffers]   (sizes fixed by the host)
+  int* sseq = reinterpret_cast<int*>(xsm + 256);
+  const size_t seq_bytes = ((size_t)p.ntiles * 4 + 127) & ~(size_t)127;
+  double* cts = reinterpret_cast<double*>(xsm + 256 + seq_bytes);
+  const size_t ct_bytes = ((size_t)(p.ncolmax + 1) * ct_ld * 8 + 127) & ~(size_t)127;
+  double* stages = reinterpret_cast<double*>(xsm + 256 + seq_bytes + ct_bytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -180,15 +184,21 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
     // ===== producer warpgroup: one lane streams the tiles of every item of this CTA through the ring =====
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(XK_PRODUCER_REGS));
     if (warp == XK_CONSUMER_WARPS && lane == 0) {
-      long q = 0;
+      int st = 0;
+      uint32_t ph = 1;  // parity of the "previous round released" phase; the first round needs no wait
+      bool first_round = true;
       for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
         const long P = item / p.nslices;
         const double* src = p.Bt + P * (long)p.ntiles * TILE_ELEMS;
-        for (int k = 0; k < p.ntiles; ++k, ++q) {
-          const int st = (int)(q % S);
-          if (q >= S) mbar_wait(&empty[st], (uint32_t)((q / S - 1) & 1));
+        for (int k = 0; k < p.ntiles; ++k) {
+          if (!first_round) mbar_wait(&empty[st], ph);
           mbar_expect_tx(&full[st], TILE_BYTES);
           bulk_g2s(stages + (size_t)st * TILE_ELEMS, src + (long)k * TILE_ELEMS, TILE_BYTES, &full[st]);
+          if (++st == S) {
+            st = 0;
+            ph ^= 1u;
+            first_round = false;
+          }
         }
       }
     }
@@ -206,6 +216,7 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
       for (int m = tid; m < p.n_ld; m += XK_CONSUMER_WARPS * 32) dst[m] = 0.0;
     }
   }
+  for (int k = tid; k < p.ntiles; k += XK_CONSUMER_WARPS * 32) sseq[k] = p.seq[k];
   asm volatile("bar.sync 1, %0;" ::"r"(XK_CONSUMER_WARPS * 32) : "memory");
 
   const int gq = lane >> 2, tq = lane & 3;
@@ -226,19 +237,19 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
 #pragma unroll
       for (int ni = 0; ni < NB; ++ni) X[s][mi][ni][0] = X[s][mi][ni][1] = 0.0;
 
-  long q = 0;
+  int st = 0;
+  uint32_t ph = 0;
   for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
     const long P = item / p.nslices;
-    for (int k = 0; k < p.ntiles; ++k, ++q) {
-      const int ij = __ldg(p.seq + k);
+    for (int k = 0; k < p.ntiles; ++k) {
+      const int ij = sseq[k];
       const int I = ij >> 16, J = ij & 0xffff;
       const bool do_row = (I & 7) == warp;
       const bool do_col = ((J & 7) == warp) && (I != J);
-      const int st = (int)(q % S);
       // Every consumer warp waits on, and releases, every tile - also those it has no task on.  A parity wait
       // only tells the current phase from the previous one, so all waiters must stay within one round of a
       // stage; gating the refill on all 8 warps guarantees that (and costs two shared-memory ops per tile).
-      mbar_wait(&full[st], (uint32_t)((q / S) & 1));
+      mbar_wait(&full[st], ph);
       if (do_row || do_col) {
         const double* tile = stages + (size_t)st * TILE_ELEMS;
         if (do_row) {
@@ -256,29 +267,37 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[st]);
+      if (++st == S) {
+        st = 0;
+        ph ^= 1u;
+      }
     }
-    // write this warp's panels of X[P] and reset the accumulators
-    double* xo = p.X + ((size_t)P * p.Ntot + col0) * p.n_ld;
+    // write this warp's panels of X[P] (group-major layout) and reset the accumulators
 #pragma unroll
-    for (int s = 0; s < NSLOT; ++s) {
-      const int I = 8 * s + warp;
+    for (int ni = 0; ni < NB; ++ni)
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+      for (int r = 0; r < 2; ++r) {
+        const int i = 8 * ni + 2 * tq + r;
+        const bool col_ok = i < ncol;
+        double* xo = p.X;
+        if (col_ok) xo += __ldg(p.xbase + col0 + i) + P * __ldg(p.xstride + col0 + i) + gq;
 #pragma unroll
-        for (int ni = 0; ni < NB; ++ni)
+        for (int s = 0; s < NSLOT; ++s) {
+          const int I = 8 * s + warp;
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            const int i = 8 * ni + 2 * tq + r;
-            if (I < p.nb && i < ncol) xo[(size_t)i * p.n_ld + 32 * I + 8 * mi + gq] = X[s][mi][ni][r];
+          for (int mi = 0; mi < 4; ++mi) {
+            if (col_ok && I < p.nb) xo[32 * I + 8 * mi] = X[s][mi][ni][r];
             X[s][mi][ni][r] = 0.0;
           }
-    }
+        }
+      }
   }
 }
 
 // Obviously-correct variant (option "jk_variant" = 1): one CTA per (P, panel), CUDA cores.
 __global__ void symm_panel_simple_kernel(const double* __restrict__ Bt, const int* __restrict__ inv,
-                                         const double* __restrict__ Ct, double* __restrict__ X, int ntiles,
+                                         const double* __restrict__ Ct, double* __restrict__ X,
+                                         const long* __restrict__ xbase, const long* __restrict__ xstride, int ntiles,
                                          int nb, int n_ld, int Ntot) {
   const int P = blockIdx.y, I = blockIdx.x;
   const double* bp = Bt + (long)P * ntiles * TILE_ELEMS;
@@ -293,28 +312,26 @@ __global__ void symm_panel_simple_kernel(const double* __restrict__ Bt, const in
       else b = bp[(long)inv[Jn * nb + I] * TILE_ELEMS + tile_swz(c, r)];
       s += b * Ct[(long)i * n_ld + nu];
     }
-    X[((long)P * Ntot + i) * n_ld + mu] = s;
+    X[xbase[i] + (long)P * xstride[i] + mu] = s;
   }
 }
 
-// rho[set][P] (+)= sum_{i in set} sum_mu X[P][i][mu] * Wt[i][mu]   (Wt = sign_i * Ct)
-__global__ void rho_kernel(const double* __restrict__ X, const double* __restrict__ Wt, double* __restrict__ rho,
-                           int naux, int n_ld, int Ntot, int nset, const int* __restrict__ set_begin,
-                           int accumulate) {
+// rho[set][P] = sum_{i in set} sum_mu X[P][i][mu] * Wt[i][mu]   (Wt = sign_i * Ct; X in the group-major layout)
+__global__ void rho_kernel(const double* __restrict__ X, const long* __restrict__ xbase,
+                           const long* __restrict__ xstride, const double* __restrict__ Wt, double* __restrict__ rho,
+                           int naux, int n_ld, int nset, const int* __restrict__ set_begin) {
   __shared__ double red[32];
   const int P = blockIdx.x;
   for (int s = 0; s < nset; ++s) {
     const int i0 = set_begin[s], i1 = set_begin[s + 1];
-    const double* x = X + ((long)P * Ntot + i0) * n_ld;
-    const double* w = Wt + (long)i0 * n_ld;
-    const long cnt = (long)(i1 - i0) * n_ld;
     double v = 0.0;
-    for (long e = threadIdx.x; e < cnt; e += blockDim.x) v += x[e] * w[e];
-    v = block_sum(v, red);
-    if (threadIdx.x == 0) {
-      if (accumulate) rho[(long)s * naux + P] += v;
-      else rho[(long)s * naux + P] = v;
+    for (int i = i0; i < i1; ++i) {
+      const double* x = X + xbase[i] + (long)P * xstride[i];
+      const double* w = Wt + (long)i * n_ld;
+      for (int e = threadIdx.x; e < n_ld; e += blockDim.x) v = fma(x[e], w[e], v);
     }
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) rho[(long)s * naux + P] = v;
   }
 }
 

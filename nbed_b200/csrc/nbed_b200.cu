@@ -178,6 +178,12 @@ struct nbd_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cusolverDnHandle_t solver = nullptr;
+  // side stream (+ its own cuSOLVER handle): runs the HBM-bound J pass next to the tensor-bound K Gram, and the
+  // second spin's eigensolve next to the first
+  cudaStream_t stream2 = nullptr;
+  cusolverDnHandle_t solver2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int overlap = 1;
   std::string err;
   long launches = 0;
   StageTimers timers;
@@ -202,14 +208,15 @@ struct nbd_ctx {
   // ---- J/K workspaces ----
   DBuf<double> d_orb, d_wt, d_X, d_rho, d_jpart, d_jk;  // d_jk = [J sets | K sets] contiguous (all-reduce buffer)
   DBuf<int> d_setbegin;
+  DBuf<long> d_xtab;  // group-major layout tables of the half-transformed tensor: [xbase | xstride]
 
   // ---- SCF problem ----
   bool scf_ready = false;
   int nspin = 0, projector = 0;
   int nelec[2] = {0, 0};
   double mu = 0.0;
-  DBuf<double> S, Xh, hcore, heff, GS, F, Huz, vhf, FG, T1, T2, Ct, D, Dold, evals, eigwork, red_part, red_out, Corth,
-      Ssave, dm0f;
+  DBuf<double> S, Xh, hcore, heff, GS, F, Huz, vhf, FG, T1, T2, Ct, D, Dold, evals, eigwork, eigwork2, red_part, red_out,
+      Corth, Ssave, Ssave2, dm0f;
   DBuf<int> devinfo;
   DiisState diis;
   // bench state
@@ -233,14 +240,14 @@ static inline dim3 grid1(long cnt, int block) { return dim3((unsigned)((cnt + bl
 // ------------------------------------------------------------------------------------------------
 static void gemm(nbd_ctx* c, int M, int N, int K, const double* A, long a_is, long a_ks, const double* B, long b_js,
                  long b_ks, double* C, long ldc, double alpha, double beta, int batch = 1, long sA = 0, long sB = 0,
-                 long sC = 0, int lower = 0, int a_kb = 0, long a_kos = 0, int b_kb = 0, long b_kos = 0) {
+                 long sC = 0, int lower = 0) {
   GemmArgs g{};
   g.M = M; g.N = N; g.K = K;
-  g.A = A; g.a_is = a_is; g.a_ks = a_ks; g.a_kb = a_kb; g.a_kos = a_kos;
-  g.B = B; g.b_js = b_js; g.b_ks = b_ks; g.b_kb = b_kb; g.b_kos = b_kos;
+  g.A = A; g.a_is = a_is; g.a_ks = a_ks;
+  g.B = B; g.b_js = b_js; g.b_ks = b_ks;
   g.C = C; g.ldc = ldc; g.alpha = alpha; g.beta = beta;
   g.batch = batch; g.strideA = sA; g.strideB = sB; g.strideC = sC; g.lower_only = lower;
-  NBD_CUDA(launch_gemm(c->stream, g, c->gemm_variant, &c->launches));
+  NBD_CUDA(launch_gemm(c->stream, g, c->gemm_variant, &c->launches, c->sm_count));
 }
 // C[M][N] = alpha * A[M][K] * B[K][N] + beta * C   (all row-major, leading dimensions given)
 static void gemm_nn(nbd_ctx* c, int M, int N, int K, const double* A, long lda, const double* B, long ldb, double* C,
@@ -289,24 +296,58 @@ static void launch_symm_panel(nbd_ctx* c, const XArgs& a, int grid, size_t smem)
   LAUNCH_CHECK(c);
 }
 
-// X[p][i][mu] for aux rows [p0, p0+np) and all Ntot orbital rows of d_orb ([Ntot][n_ld]).
+// Group-major layout of the half-transformed tensor for a chunk of np aux rows: the columns of group g
+// ([c0, c1), width w) form a dense [np * w][n_ld] matrix (row = (P, i)), so the Gram / second half-transform
+// GEMMs see a plain strided operand.  Returns the offset of each group; fills the device tables.
+struct XLayout {
+  std::vector<long> group_base;
+  long total = 0;
+};
+static XLayout make_xlayout(nbd_ctx* c, int np, int Ntot, const std::vector<std::pair<int, int>>& groups) {
+  XLayout L;
+  std::vector<long> xb(std::max(1, Ntot), 0), xs(std::max(1, Ntot), 0);
+  long base = 0;
+  int covered = 0;
+  for (auto& g : groups) {
+    const int w = g.second - g.first;
+    NBD_REQUIRE(g.first == covered && w >= 0, NBD_ERR_STATE, "orbital groups must tile the column range");
+    L.group_base.push_back(base);
+    for (int i = g.first; i < g.second; ++i) {
+      xb[i] = base + (long)(i - g.first) * c->n_ld;
+      xs[i] = (long)w * c->n_ld;
+    }
+    base += (long)np * w * c->n_ld;
+    covered = g.second;
+  }
+  NBD_REQUIRE(covered == Ntot, NBD_ERR_STATE, "orbital groups cover %d of %d columns", covered, Ntot);
+  L.total = base;
+  long* d = c->d_xtab.ensure((size_t)2 * std::max(1, Ntot));
+  NBD_CUDA(cudaMemcpyAsync(d, xb.data(), sizeof(long) * Ntot, cudaMemcpyHostToDevice, c->stream));
+  NBD_CUDA(cudaMemcpyAsync(d + Ntot, xs.data(), sizeof(long) * Ntot, cudaMemcpyHostToDevice, c->stream));
+  return L;
+}
+
+// X (group-major, tables in c->d_xtab) for aux rows [p0, p0+np) and all Ntot orbital rows of d_orb ([Ntot][n_ld]).
 static void half_transform(nbd_ctx* c, int p0, int np, const double* d_orb, int Ntot, double* d_X) {
+  const long* xbase = c->d_xtab.p;
+  const long* xstride = c->d_xtab.p + Ntot;
   if (c->jk_variant == 1) {
     dim3 g(c->nb, np);
     symm_panel_simple_kernel<<<g, 256, 0, c->stream>>>(c->Bt + (long)p0 * c->ntiles * TILE_ELEMS, c->d_inv.p, d_orb,
-                                                        d_X, c->ntiles, c->nb, c->n_ld, Ntot);
+                                                        d_X, xbase, xstride, c->ntiles, c->nb, c->n_ld, Ntot);
     LAUNCH_CHECK(c);
     return;
   }
   const int nslot = (c->nb + 7) / 8;
   NBD_REQUIRE(nslot <= 12, NBD_ERR_UNSUPPORTED, "nao = %d exceeds the 3072-AO envelope of the panel kernel", c->nao);
+  const size_t seq_bytes = ((size_t)c->ntiles * 4 + 127) & ~(size_t)127;
   auto smem_for = [&](int ncolmax, int stages) {
     const size_t ct = (((size_t)(ncolmax + 1) * (c->n_ld + 4) * 8) + 127) & ~(size_t)127;
-    return (size_t)256 + ct + (size_t)stages * TILE_BYTES;
+    return (size_t)256 + seq_bytes + ct + (size_t)stages * TILE_BYTES;
   };
   int NBsel = (Ntot > 8 && nslot <= 6) ? 2 : 1;
-  if (NBsel == 2 && smem_for(16, 4) > c->smem_optin) NBsel = 1;
-  const int ncolmax = 8 * NBsel;
+  if (NBsel == 2 && smem_for(std::min(16, Ntot), 6) > c->smem_optin) NBsel = 1;
+  const int ncolmax = std::min(8 * NBsel, Ntot);
   NBD_REQUIRE(smem_for(ncolmax, 2) <= c->smem_optin, NBD_ERR_UNSUPPORTED, "nao = %d: orbital slice does not fit shared memory", c->nao);
   int stages = 16;
   while (stages > 2 && smem_for(ncolmax, stages) > c->smem_optin) --stages;
@@ -315,13 +356,16 @@ static void half_transform(nbd_ctx* c, int p0, int np, const double* d_orb, int 
   a.seq = c->d_seq.p;
   a.Ct = d_orb;
   a.X = d_X;
+  a.xbase = xbase;
+  a.xstride = xstride;
   a.naux = np;
   a.ntiles = c->ntiles;
   a.nb = c->nb;
   a.n_ld = c->n_ld;
   a.Ntot = Ntot;
-  a.nslices = (Ntot + ncolmax - 1) / ncolmax;
+  a.nslices = (Ntot + 8 * NBsel - 1) / (8 * NBsel);
   a.nstages = stages;
+  a.ncolmax = ncolmax;
   const long nitems = (long)np * a.nslices;
   long grid = std::min<long>(nitems, (long)c->sm_count);
   // gridDim.x must be a multiple of nslices so that a CTA keeps the same orbital slice for all its items
@@ -367,43 +411,12 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
     NBD_CUDA(cudaMemcpyAsync(c->d_setbegin.p, jbegin.data(), sizeof(int) * (njset + 1), cudaMemcpyHostToDevice, c->stream));
   }
   std::vector<bool> k_started(nkset, false);
-  for (int p0 = 0; p0 < naux; p0 += chunk) {
-    const int np = std::min(chunk, naux - p0);
-    {
-      StageScope ts(c->timers, c->stream, "jk_x");
-      half_transform(c, p0, np, d_orb, Ntot, X);
-    }
-    if (d_J) {
-      StageScope ts(c->timers, c->stream, "jk_rho");
-      rho_kernel<<<np, 256, 0, c->stream>>>(X, d_wt, rho + p0, naux, n_ld, Ntot, njset, c->d_setbegin.p, 0);
-      LAUNCH_CHECK(c);
-    }
-    if (d_K) {
-      StageScope ts(c->timers, c->stream, "jk_k");
-      // batch consecutive groups of identical width / sign belonging to consecutive sets into one launch
-      size_t gi = 0;
-      while (gi < kgroups.size()) {
-        const KGroup& g0 = kgroups[gi];
-        const int w = g0.c1 - g0.c0;
-        size_t gj = gi + 1;
-        while (gj < kgroups.size() && kgroups[gj].c1 - kgroups[gj].c0 == w && kgroups[gj].alpha == g0.alpha &&
-               kgroups[gj].set == kgroups[gj - 1].set + 1 && kgroups[gj].c0 == kgroups[gj - 1].c0 + w &&
-               k_started[kgroups[gj].set] == k_started[g0.set])
-          ++gj;
-        const int batch = (int)(gj - gi);
-        if (w > 0) {
-          const double* Xa = X + (long)g0.c0 * n_ld;
-          gemm(c, n, n, np * w, Xa, 1, n_ld, Xa, 1, n_ld, d_K + (long)g0.set * nn, n, g0.alpha,
-               k_started[g0.set] ? 1.0 : 0.0, batch, (long)w * n_ld, (long)w * n_ld, nn, /*lower=*/1, w,
-               (long)Ntot * n_ld, w, (long)Ntot * n_ld);
-          for (size_t q = gi; q < gj; ++q) k_started[kgroups[q].set] = true;
-        }
-        gi = gj;
-      }
-    }
-  }
-  if (d_J) {
-    StageScope ts(c->timers, c->stream, "jk_j");
+  // column groups of the layout: the K groups when K is wanted (they tile the columns), else one group
+  std::vector<std::pair<int, int>> cols;
+  if (d_K) for (auto& g : kgroups) cols.push_back({g.c0, g.c1});
+  else cols.push_back({0, Ntot});
+  auto j_pass = [&](cudaStream_t st) {
+    StageScope ts(c->timers, st, "jk_j");
     const long E = (long)c->ntiles * TILE_ELEMS, E2 = E / 2;
     const int bx = (int)((E2 + 255) / 256);
     int nsplit = (int)std::min<long>(std::min(naux, 64), std::max<long>(1, ((long)c->sm_count * 16 + bx - 1) / bx));
@@ -414,15 +427,63 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
       double* part = c->d_jpart.ensure((size_t)nsplit * ns * E);
       dim3 g(bx, nsplit);
       if (ns == 2)
-        j_pass_kernel<2><<<g, 256, 0, c->stream>>>((const double2*)c->Bt, rho + (long)s0 * naux, (double2*)part, E2, naux, rows_per_split);
+        j_pass_kernel<2><<<g, 256, 0, st>>>((const double2*)c->Bt, rho + (long)s0 * naux, (double2*)part, E2, naux, rows_per_split);
       else
-        j_pass_kernel<1><<<g, 256, 0, c->stream>>>((const double2*)c->Bt, rho + (long)s0 * naux, (double2*)part, E2, naux, rows_per_split);
+        j_pass_kernel<1><<<g, 256, 0, st>>>((const double2*)c->Bt, rho + (long)s0 * naux, (double2*)part, E2, naux, rows_per_split);
       LAUNCH_CHECK(c);
       dim3 gf((n + 127) / 128, n);
-      j_finalize_kernel<<<gf, 128, 0, c->stream>>>(part, c->d_inv.p, d_J + (long)s0 * nn, n, c->nb, E, nsplit, ns);
+      j_finalize_kernel<<<gf, 128, 0, st>>>(part, c->d_inv.p, d_J + (long)s0 * nn, n, c->nb, E, nsplit, ns);
       LAUNCH_CHECK(c);
     }
+  };
+  bool forked = false;
+  for (int p0 = 0; p0 < naux; p0 += chunk) {
+    const int np = std::min(chunk, naux - p0);
+    const bool last = p0 + np >= naux;
+    const XLayout L = make_xlayout(c, np, Ntot, cols);
+    {
+      StageScope ts(c->timers, c->stream, "jk_x");
+      half_transform(c, p0, np, d_orb, Ntot, X);
+    }
+    if (d_J) {
+      StageScope ts(c->timers, c->stream, "jk_rho");
+      rho_kernel<<<np, 256, 0, c->stream>>>(X, c->d_xtab.p, c->d_xtab.p + Ntot, d_wt, rho + p0, naux, n_ld, njset, c->d_setbegin.p);
+      LAUNCH_CHECK(c);
+    }
+    if (d_J && last && d_K && c->overlap) {
+      // pass 2 (HBM-bound) runs on the side stream next to the tensor-bound K Gram of this chunk
+      NBD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+      NBD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+      j_pass(c->stream2);
+      NBD_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+      forked = true;
+    }
+    if (d_K) {
+      StageScope ts(c->timers, c->stream, "jk_k");
+      // K_s (+)= alpha * X_g^T X_g with X_g the dense [np * w][n_ld] matrix of group g; consecutive groups of
+      // identical width / sign that feed consecutive sets go out as one batched launch
+      size_t gi = 0;
+      while (gi < kgroups.size()) {
+        const KGroup& g0 = kgroups[gi];
+        const int w = g0.c1 - g0.c0;
+        size_t gj = gi + 1;
+        while (gj < kgroups.size() && kgroups[gj].c1 - kgroups[gj].c0 == w && kgroups[gj].alpha == g0.alpha &&
+               kgroups[gj].set == kgroups[gj - 1].set + 1 && k_started[kgroups[gj].set] == k_started[g0.set])
+          ++gj;
+        const int batch = (int)(gj - gi);
+        if (w > 0) {
+          const double* Xa = X + L.group_base[gi];
+          const long gstride = (long)np * w * n_ld;  // equal-width groups are laid out back to back
+          gemm(c, n, n, np * w, Xa, 1, n_ld, Xa, 1, n_ld, d_K + (long)g0.set * nn, n, g0.alpha,
+               k_started[g0.set] ? 1.0 : 0.0, batch, gstride, gstride, nn, /*lower=*/1);
+          for (size_t q = gi; q < gj; ++q) k_started[kgroups[q].set] = true;
+        }
+        gi = gj;
+      }
+    }
   }
+  if (d_J && !forked) j_pass(c->stream);
+  if (forked) NBD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   if (d_K) symmetrize_lower(c, d_K, n, nkset);
 }
 
@@ -448,19 +509,22 @@ static void eigh_batched(nbd_ctx* c, double* A, double* w, int n, int batch) {
   // numpy.linalg.eigh reads the lower triangle of the row-major matrix == the UPPER triangle column-major
   NBD_SOLVER(cusolverDnDsyevd_bufferSize(c->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A, n, w, &lwork));
   double* work = c->eigwork.ensure((size_t)lwork);
+  double* work2 = c->eigwork2.ensure((size_t)lwork);
   int* info = c->devinfo.ensure(8);
-  for (int b = 0; b < batch; ++b)
-    NBD_SOLVER(cusolverDnDsyevd(c->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A + (long)b * n * n, n,
-                                w + (long)b * n, work, lwork, info + b));
-}
-// generalised A x = w B x (scipy.linalg.eigh(f, s)); Bm is overwritten by its Cholesky factor.
-static void eigh_generalized(nbd_ctx* c, double* A, double* Bm, double* w, int n) {
-  StageScope ts(c->timers, c->stream, "eigh");
-  int lwork = 0;
-  NBD_SOLVER(cusolverDnDsygvd_bufferSize(c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A, n, Bm, n, w, &lwork));
-  double* work = c->eigwork.ensure((size_t)lwork);
-  int* info = c->devinfo.ensure(8);
-  NBD_SOLVER(cusolverDnDsygvd(c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A, n, Bm, n, w, work, lwork, info));
+  const bool par = c->overlap && batch == 2;
+  if (par) {
+    NBD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    NBD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  }
+  for (int b = 0; b < batch; ++b) {
+    const bool side = par && b == 1;
+    NBD_SOLVER(cusolverDnDsyevd(side ? c->solver2 : c->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n,
+                                A + (long)b * n * n, n, w + (long)b * n, side ? work2 : work, lwork, info + b));
+  }
+  if (par) {
+    NBD_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+    NBD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  }
 }
 static void check_devinfo(nbd_ctx* c, int count, const char* what) {
   int h[8] = {0};
@@ -521,6 +585,11 @@ int nbd_create(nbd_ctx** out, int device) {
     NBD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     NBD_SOLVER(cusolverDnCreate(&c->solver));
     NBD_SOLVER(cusolverDnSetStream(c->solver, c->stream));
+    NBD_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    NBD_SOLVER(cusolverDnCreate(&c->solver2));
+    NBD_SOLVER(cusolverDnSetStream(c->solver2, c->stream2));
+    NBD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    NBD_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   } catch (const Error& e) {
     fprintf(stderr, "nbd_create: %s\n", e.msg.c_str());
     int code = e.code;
@@ -538,6 +607,10 @@ int nbd_destroy(nbd_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   if (c->Bt) cudaFree(c->Bt);
   if (c->solver) cusolverDnDestroy(c->solver);
+  if (c->solver2) cusolverDnDestroy(c->solver2);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return NBD_OK;
@@ -552,6 +625,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "gemm_variant") c->gemm_variant = (int)value;
   else if (k == "x_budget_mb") c->x_budget_bytes = value << 20;
   else if (k == "timers") c->timers.enabled = value != 0;
+  else if (k == "overlap") c->overlap = (int)value;
   else return NBD_ERR_ARG;
   return NBD_OK;
 }

@@ -380,14 +380,34 @@ static double mu_energy(nbd_ctx* c, double e_nuc) {
   return e1 + 0.5 * ec + e_nuc;
 }
 
-// generalised eigensolve per spin of c->F (copied), rows of Ct = MOs
+// generalised eigensolve per spin of Fsrc (copied), rows of Crows = MOs; the two spins run on the two streams
 static void mu_eig(nbd_ctx* c, const double* Fsrc, double* Crows) {
   const int n = c->nao;
   const long nn = (long)n * n;
+  StageScope ts(c->timers, c->stream, "eigh");
+  int lwork = 0;
+  NBD_SOLVER(cusolverDnDsygvd_bufferSize(c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, Crows, n, c->Ssave.p, n, c->evals.p, &lwork));
+  double* work[2] = {c->eigwork.ensure((size_t)lwork), c->eigwork2.ensure((size_t)lwork)};
+  double* sv[2] = {c->Ssave.ensure(nn), c->Ssave2.ensure(nn)};
+  int* info = c->devinfo.ensure(8);
+  const bool par = c->overlap && c->nspin == 2;
+  NBD_CUDA(cudaMemcpyAsync(Crows, Fsrc, sizeof(double) * nn * c->nspin, cudaMemcpyDeviceToDevice, c->stream));
+  if (par) {
+    NBD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    NBD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  }
   for (int s = 0; s < c->nspin; ++s) {
-    NBD_CUDA(cudaMemcpyAsync(Crows + s * nn, Fsrc + s * nn, sizeof(double) * nn, cudaMemcpyDeviceToDevice, c->stream));
-    NBD_CUDA(cudaMemcpyAsync(c->Ssave.p, c->S.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, c->stream));
-    eigh_generalized(c, Crows + s * nn, c->Ssave.p, c->evals.p + (long)s * n, n);
+    const bool side = par && s == 1;
+    cudaStream_t st = side ? c->stream2 : c->stream;
+    // scipy.linalg.eigh(f, s): dsygvd overwrites the overlap with its Cholesky factor -> work on a copy
+    NBD_CUDA(cudaMemcpyAsync(sv[side], c->S.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+    NBD_SOLVER(cusolverDnDsygvd(side ? c->solver2 : c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                CUBLAS_FILL_MODE_UPPER, n, Crows + s * nn, n, sv[side], n, c->evals.p + (long)s * n,
+                                work[side], lwork, info + s));
+  }
+  if (par) {
+    NBD_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+    NBD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   }
 }
 
@@ -505,7 +525,7 @@ extern "C" int nbd_mu_scf(nbd_ctx* c, int max_cycle, double conv_tol, double e_n
       scalars(e_tot);
       conv = (std::fabs(e_tot - last_e) < conv_tol * 10 || norm_g < conv_tol_grad * 3) ? 1 : 0;
     }
-    check_devinfo(c, 1, "generalised eigensolve");
+    check_devinfo(c, c->nspin, "generalised eigensolve");
     scf_export(c, mo_coeff, mo_energy, dm, vhf_out, c->vhf.p);
     if (mo_occ)
       for (int s = 0; s < ns; ++s)
