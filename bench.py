@@ -202,8 +202,9 @@ def run_b200(args):
     if world > 1:
         ctx.comm_init_from_torch()
     # contiguous aux shard of this rank
-    lo = naux * rank // world
-    hi = naux * (rank + 1) // world
+    from nbed_b200.sharding import aux_shard
+
+    lo, hi = aux_shard(naux, rank, world)
     ctx.cderi_alloc(n, hi - lo)
     ctx.cderi_synth(p.seed, p.scale, lo)  # stated boundary: integrals are generated once, outside the timed loop
     log(f"3-centre tensor shard [{lo}, {hi}) of {naux} rows resident ({8e-9 * (hi - lo) * n * (n + 1) / 2:.1f} GB packed)")

@@ -1,0 +1,118 @@
+"""CPU: the oracle against the reference's golden vectors and against outputs of the unmodified reference.
+
+``tests/golden/reference_runs.npz`` holds outputs of the reference's own functions (imported unmodified from
+/root/reference behind stub pyscf modules, see tests/golden/make_golden.py); ``water_sto3g.npz`` holds the
+integrals of the reference's test molecule and the golden energies of tests/test_driver.py:56-57,76."""
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+from nbed_b200 import synthetic as syn
+from oracle import fock_space as fs
+from oracle import nbed_restatement as nr
+from oracle import pyscf_restatement as ps
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SCF_CASES = [("c1", "C1_h2o_sto3g", 2.0), ("c2", "C2_h2o_ccpvdz", 3.0)]
+
+
+@pytest.fixture(scope="module")
+def runs():
+    return np.load(os.path.join(GOLD, "reference_runs.npz"))
+
+
+@pytest.fixture(scope="module")
+def water():
+    return np.load(os.path.join(GOLD, "water_sto3g.npz"))
+
+
+def scf_problem(key, scale):
+    cfg = dict(syn.CONFIGS[key])
+    p = syn.make_problem(seed=0, scale=scale / np.sqrt(cfg["n"] * cfg["naux"]), **cfg)
+    return p, p.cderi()
+
+
+@pytest.mark.parametrize("name,key,scale", SCF_CASES)
+@pytest.mark.parametrize("diis", [True, False])
+def test_oracle_huzinaga_uhf_matches_reference_run(runs, name, key, scale, diis):
+    p, b = scf_problem(key, scale)
+    mf = ps.DFUHF(p.ovlp, p.hcore, b, p.nelec, max_cycle=40, conv_tol=1e-8)
+    c, e, d, h, conv = nr.huzinaga_scf(mf, p.v_emb, p.dm_enviro, use_DIIS=diis)
+    tag = f"{name}_uhf_diis{int(diis)}"
+    assert conv == bool(runs[f"{tag}_conv"]) and mf.n_jk_builds == int(runs[f"{tag}_ncall"])
+    assert np.abs(e - runs[f"{tag}_e"]).max() < 1e-11
+    assert np.abs(np.asarray(d) - runs[f"{tag}_dm"]).max() < 1e-11
+    assert np.abs(h - runs[f"{tag}_huz"]).max() < 1e-11
+    assert np.abs(np.abs(c) - runs[f"{tag}_cabs"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("name,key,scale", SCF_CASES)
+def test_oracle_huzinaga_rhf_and_guess_match_reference_run(runs, name, key, scale):
+    p, b = scf_problem(key, scale)
+    mf = ps.DFRHF(p.ovlp, p.hcore, b, p.nelec, max_cycle=40, conv_tol=1e-8)
+    c, e, d, h, conv = nr.huzinaga_scf(mf, p.v_emb[0], 2.0 * p.dm_enviro[0])
+    assert conv == bool(runs[f"{name}_rhf_conv"]) and mf.n_jk_builds == int(runs[f"{name}_rhf_ncall"])
+    assert np.abs(e - runs[f"{name}_rhf_e"]).max() < 1e-11
+    assert np.abs(np.asarray(d) - runs[f"{name}_rhf_dm"]).max() < 1e-11
+    assert np.abs(h - runs[f"{name}_rhf_huz"]).max() < 1e-11
+    rng = np.random.default_rng(5)
+    r = rng.normal(size=(2, p.n, p.n)) * 1e-3
+    dm0 = runs[f"{name}_uhf_diis1_dm"] + r + r.transpose(0, 2, 1)
+    mf = ps.DFUHF(p.ovlp, p.hcore, b, p.nelec, max_cycle=40, conv_tol=1e-8)
+    c, e, d, h, conv = nr.huzinaga_scf(mf, p.v_emb, p.dm_enviro, dm_initial_guess=dm0)
+    assert mf.n_jk_builds == int(runs[f"{name}_uhf_guess_ncall"])
+    assert np.abs(np.asarray(d) - runs[f"{name}_uhf_guess_dm"]).max() < 1e-11
+    mf = ps.DFUHF(p.ovlp, p.hcore, b, p.nelec)
+    ee = nr.energy_elec(mf, runs[f"{name}_uhf_diis1_dm"], p.hcore + p.v_emb, None)
+    assert np.abs(np.array(ee) - runs[f"{name}_energy_elec"]).max() < 1e-11
+
+
+def test_oracle_small_functions_match_reference_run(runs):
+    rng = np.random.default_rng(11)
+    f3, g3 = rng.normal(size=(2, 9, 9)), rng.normal(size=(2, 9, 9))
+    assert np.array_equal(nr.get_huzinaga_operator(f3, g3, np.zeros_like(g3)), runs["huzop_rank3"])
+    assert np.array_equal(nr.get_huzinaga_operator(f3[0], g3[0], np.zeros_like(g3[0])), runs["huzop_rank2"])
+    one = rng.normal(size=(2, 3, 3))
+    two = rng.normal(size=(4, 3, 3, 3, 3))
+    two[0, 0, 1, 2, 0] = 0.99e-8
+    two[2, 2, 1, 0, 1] = -1.01e-8
+    one[1, 2, 0] = 5e-9
+    h1, h2 = nr.spinorb_from_spatial(one, two)
+    assert np.array_equal(h1, runs["spinorb_h1"]) and np.array_equal(h2, runs["spinorb_h2"])
+
+
+def test_oracle_pinned_on_water_sto3g_goldens(water):
+    """E_nuc, UHF and FCI energies of the reference's test molecule (tests/test_driver.py:56-57,76).
+
+    The exact ERI enters the density-fitted code path through its full-rank Cholesky vectors, so this also pins
+    df_get_jk, the pyscf kernel() restatement, the DF ao2mo and the spin-orbital packing."""
+    s, h, eri, e_nuc = water["S"], water["hcore"], water["eri"], float(water["e_nuc"])
+    assert abs(e_nuc - float(water["ref_e_nuc"])) < 1e-12
+    b = ps.cholesky_eri_exact(eri)
+    npair = 28
+    il = np.tril_indices(7)
+    assert np.abs(b.T @ b - eri[il[0], il[1]][:, il[0], il[1]]).max() < 1e-12 and b.shape[1] == npair
+    _, c = scipy.linalg.eigh(h, s)
+    mf = ps.DFUHF(s, h, b, (5, 5), e_nuc=e_nuc, conv_tol=1e-11)
+    conv, e_uhf = ps.scf_kernel(mf, conv_tol=1e-11, dm0=np.array([c[:, :5] @ c[:, :5].T] * 2))[:2]
+    assert conv and abs(e_uhf - float(water["ref_e_uhf"])) < 1e-7  # reference converged to conv_tol = 1e-9
+    const, h1, h2 = nr.build_hamiltonian(mf, b, e_nuc, restricted=False)
+    e_fci = fs.ground_energies(const, h1, h2, k=1)[0]
+    assert abs(e_fci - float(water["ref_e_fci"])) < 1e-7
+
+
+def test_oracle_jk_dense_and_orbital_branches_agree():
+    p, b = scf_problem("C2_h2o_ccpvdz", 3.0)
+    rng = np.random.default_rng(0)
+    orbs = [rng.normal(size=(p.n, 4)), rng.normal(size=(p.n, 3))]
+    vj, vk = ps.df_get_jk_occ(b, orbs)
+    dj, dk = ps.df_get_jk(b, np.array([o @ o.T for o in orbs]))
+    assert np.abs(vj - dj).max() < 1e-12 and np.abs(vk - dk).max() < 1e-12
+    # exact 4-index contraction of the DF integrals
+    full = ps.unpack_tril(b, p.n)
+    eri = np.einsum("pij,pkl->ijkl", full, full)
+    dm = np.array([o @ o.T for o in orbs])
+    assert np.abs(vj - np.einsum("ijkl,skl->sij", eri, dm)).max() < 1e-12
+    assert np.abs(vk - np.einsum("ikjl,skl->sij", eri, dm)).max() < 1e-12

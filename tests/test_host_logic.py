@@ -1,0 +1,101 @@
+"""CPU: the C-ABI library loads and exports every declared symbol; host-side helpers; the bench reference arm."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    from nbed_b200 import _lib, build
+
+    build.build_library()  # no-op when up to date; nvcc cross-compiles sm_100a without a GPU
+    lib = _lib.load()
+    assert lib.nbd_version() >= 100
+    header = open(os.path.join(ROOT, "include", "nbed_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(nbd_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from nbed_b200 import B200Context, NbdError
+
+    with pytest.raises(NbdError):
+        B200Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "nbed_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_aux_shards_tile_the_index():
+    from nbed_b200.sharding import aux_shard
+
+    for naux in (0, 1, 7, 4128, 4129):
+        for world in (1, 2, 3, 8):
+            edges = [aux_shard(naux, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == naux
+            assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        aux_shard(10, 2, 2)
+
+
+def test_synthetic_tensor_is_counter_based():
+    from nbed_b200 import synthetic as syn
+
+    full = syn.synth_cderi_rows(3, 9, 0.5, np.arange(12))
+    part = syn.synth_cderi_rows(3, 9, 0.5, np.array([4, 11]))
+    assert np.array_equal(part, full[[4, 11]])
+    assert full.min() >= -0.5 and full.max() < 0.5 and abs(full.mean()) < 0.05
+    # known answer of the SplitMix64 stream (guards the device generator's bit-compatibility contract)
+    v = syn.hash_uniform(5, np.array([0, 1, 2 ** 40], dtype=np.uint64))
+    assert np.allclose(v, [0.9413689876, -0.7110414177, 0.7827159049], atol=1e-9), v
+    p = syn.make_problem(n=12, naux=20, nocc=3, n_env=2, seed=4)
+    assert np.abs(p.c_env[0].T @ p.ovlp @ p.c_env[0] - np.eye(2)).max() < 1e-12
+    assert p.cderi().shape == (20, 78)
+
+
+def test_diis_restatement_recovers_linear_fixed_point():
+    """pyscf.lib.diis.DIIS on x -> A x + b converges to the fixed point in <= dim + 2 steps."""
+    from oracle.pyscf_restatement import DIIS
+
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(4, 4)) * 0.3
+    b = rng.normal(size=4)
+    fix = np.linalg.solve(np.eye(4) - a, b)
+    d, x = DIIS(), np.zeros(4)
+    for _ in range(8):
+        x = d.update(a @ x + b)
+    assert np.abs(x - fix).max() < 1e-10
+
+
+def test_bench_reference_arm_emits_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C3",
+                          "--steps", "1", "--warmup", "0", "--cpu-sample-rows", "16"], capture_output=True, text=True,
+                         timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "embedded_scf_iterations_per_s"
+    for key in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+                "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
