@@ -28,6 +28,9 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load(std::string& why) {
     if (lib) return true;
@@ -47,7 +50,10 @@ struct NcclApi {
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString) {
+    Broadcast = (decltype(Broadcast))dlsym(lib, "ncclBroadcast");
+    GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString || !Broadcast || !GroupStart || !GroupEnd) {
       why = "libnccl is missing required symbols";
       return false;
     }
@@ -184,6 +190,7 @@ struct nbd_ctx {
   cusolverDnHandle_t solver2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int overlap = 1;
+  int dist_eig = 1;  // distribute the two spins' eigensolves over ranks 0 / 1 when a communicator exists
   std::string err;
   long launches = 0;
   StageTimers timers;
@@ -215,8 +222,8 @@ struct nbd_ctx {
   int nspin = 0, projector = 0;
   int nelec[2] = {0, 0};
   double mu = 0.0;
-  DBuf<double> S, Xh, hcore, heff, GS, F, Huz, vhf, FG, T1, T2, Ct, D, Dold, evals, eigwork, eigwork2, red_part, red_out,
-      Corth, Ssave, Ssave2, dm0f;
+  DBuf<double> S, Xh, hcore, heff, GS, F, Huz, vhf, FG, T1, T2, Ct, D, Dold, evals, eigwork, red_part, red_out,
+      Corth, Ssave, dm0f;
   DBuf<int> devinfo;
   DiisState diis;
   // bench state
@@ -503,28 +510,39 @@ static void reduce_to(nbd_ctx* c, const double* a, const double* b, long cnt, in
 // Eigensolvers (cuSOLVER; timed under "eigh")
 // ------------------------------------------------------------------------------------------------
 // A [batch][n][n] symmetric (row-major == column-major); on return rows of A = eigenvectors; w ascending.
+// With a communicator of >= 2 ranks and two matrices (the two spins), rank 0 solves the first and rank 1 the
+// second, and the eigenvectors / eigenvalues are broadcast: the replicated eigensolve is the Amdahl term of the
+// sharded iteration, this halves it (and makes the orbitals bit-identical on all ranks).
+static bool eig_distributed(const nbd_ctx* c, int batch) { return c->world >= 2 && c->comm && batch == 2 && c->dist_eig; }
+static void eig_exchange(nbd_ctx* c, double* A, double* w, int n) {
+  const long nn = (long)n * n;
+  StageScope ts(c->timers, c->stream, "eig_bcast");
+  ncclResult_t r = g_nccl.GroupStart();
+  for (int b = 0; b < 2 && r == ncclSuccess; ++b) {
+    r = g_nccl.Broadcast(A + b * nn, A + b * nn, (size_t)nn, ncclDouble, b, c->comm, c->stream);
+    if (r == ncclSuccess) r = g_nccl.Broadcast(w + (long)b * n, w + (long)b * n, (size_t)n, ncclDouble, b, c->comm, c->stream);
+  }
+  if (r == ncclSuccess) r = g_nccl.GroupEnd();
+  if (r != ncclSuccess) fail(NBD_ERR_CUDA, "ncclBroadcast (eigenvectors): %s", g_nccl.GetErrorString(r));
+}
+
 static void eigh_batched(nbd_ctx* c, double* A, double* w, int n, int batch) {
-  StageScope ts(c->timers, c->stream, "eigh");
   int lwork = 0;
   // numpy.linalg.eigh reads the lower triangle of the row-major matrix == the UPPER triangle column-major
   NBD_SOLVER(cusolverDnDsyevd_bufferSize(c->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A, n, w, &lwork));
   double* work = c->eigwork.ensure((size_t)lwork);
-  double* work2 = c->eigwork2.ensure((size_t)lwork);
   int* info = c->devinfo.ensure(8);
-  const bool par = c->overlap && batch == 2;
-  if (par) {
-    NBD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
-    NBD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  NBD_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 8, c->stream));
+  const bool dist = eig_distributed(c, batch);
+  {
+    StageScope ts(c->timers, c->stream, "eigh");
+    for (int b = 0; b < batch; ++b) {
+      if (dist && b != c->rank) continue;
+      NBD_SOLVER(cusolverDnDsyevd(c->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A + (long)b * n * n, n,
+                                  w + (long)b * n, work, lwork, info + b));
+    }
   }
-  for (int b = 0; b < batch; ++b) {
-    const bool side = par && b == 1;
-    NBD_SOLVER(cusolverDnDsyevd(side ? c->solver2 : c->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n,
-                                A + (long)b * n * n, n, w + (long)b * n, side ? work2 : work, lwork, info + b));
-  }
-  if (par) {
-    NBD_CUDA(cudaEventRecord(c->ev_join, c->stream2));
-    NBD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-  }
+  if (dist) eig_exchange(c, A, w, n);
 }
 static void check_devinfo(nbd_ctx* c, int count, const char* what) {
   int h[8] = {0};
@@ -626,6 +644,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "x_budget_mb") c->x_budget_bytes = value << 20;
   else if (k == "timers") c->timers.enabled = value != 0;
   else if (k == "overlap") c->overlap = (int)value;
+  else if (k == "dist_eig") c->dist_eig = (int)value;
   else return NBD_ERR_ARG;
   return NBD_OK;
 }

@@ -380,35 +380,30 @@ static double mu_energy(nbd_ctx* c, double e_nuc) {
   return e1 + 0.5 * ec + e_nuc;
 }
 
-// generalised eigensolve per spin of Fsrc (copied), rows of Crows = MOs; the two spins run on the two streams
+// generalised eigensolve per spin of Fsrc (copied), rows of Crows = MOs (spins distributed over ranks 0 / 1
+// when a communicator exists, see eigh_batched)
 static void mu_eig(nbd_ctx* c, const double* Fsrc, double* Crows) {
   const int n = c->nao;
   const long nn = (long)n * n;
-  StageScope ts(c->timers, c->stream, "eigh");
   int lwork = 0;
-  NBD_SOLVER(cusolverDnDsygvd_bufferSize(c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, Crows, n, c->Ssave.p, n, c->evals.p, &lwork));
-  double* work[2] = {c->eigwork.ensure((size_t)lwork), c->eigwork2.ensure((size_t)lwork)};
-  double* sv[2] = {c->Ssave.ensure(nn), c->Ssave2.ensure(nn)};
+  double* sv = c->Ssave.ensure(nn);
+  NBD_SOLVER(cusolverDnDsygvd_bufferSize(c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, Crows, n, sv, n, c->evals.p, &lwork));
+  double* work = c->eigwork.ensure((size_t)lwork);
   int* info = c->devinfo.ensure(8);
-  const bool par = c->overlap && c->nspin == 2;
+  NBD_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 8, c->stream));
   NBD_CUDA(cudaMemcpyAsync(Crows, Fsrc, sizeof(double) * nn * c->nspin, cudaMemcpyDeviceToDevice, c->stream));
-  if (par) {
-    NBD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
-    NBD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  const bool dist = eig_distributed(c, c->nspin);
+  {
+    StageScope ts(c->timers, c->stream, "eigh");
+    for (int s = 0; s < c->nspin; ++s) {
+      if (dist && s != c->rank) continue;
+      // scipy.linalg.eigh(f, s): dsygvd overwrites the overlap with its Cholesky factor -> work on a copy
+      NBD_CUDA(cudaMemcpyAsync(sv, c->S.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, c->stream));
+      NBD_SOLVER(cusolverDnDsygvd(c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n,
+                                  Crows + s * nn, n, sv, n, c->evals.p + (long)s * n, work, lwork, info + s));
+    }
   }
-  for (int s = 0; s < c->nspin; ++s) {
-    const bool side = par && s == 1;
-    cudaStream_t st = side ? c->stream2 : c->stream;
-    // scipy.linalg.eigh(f, s): dsygvd overwrites the overlap with its Cholesky factor -> work on a copy
-    NBD_CUDA(cudaMemcpyAsync(sv[side], c->S.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
-    NBD_SOLVER(cusolverDnDsygvd(side ? c->solver2 : c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
-                                CUBLAS_FILL_MODE_UPPER, n, Crows + s * nn, n, sv[side], n, c->evals.p + (long)s * n,
-                                work[side], lwork, info + s));
-  }
-  if (par) {
-    NBD_CUDA(cudaEventRecord(c->ev_join, c->stream2));
-    NBD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-  }
+  if (dist) eig_exchange(c, Crows, c->evals.p, n);
 }
 
 // ||g||, g_s = C_vir^T F_s C_occ   (pyscf/scf/uhf.py:get_grad)
