@@ -13,6 +13,8 @@
 #ifndef NBED_B200_H
 #define NBED_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -43,6 +45,10 @@ int nbd_set_option(nbd_ctx* ctx, const char* key, long value);
 double nbd_timer_ms(nbd_ctx* ctx, const char* key);
 /* Number of kernels launched by this library since the context was created (bench "gpu_launches"). */
 long nbd_launch_count(nbd_ctx* ctx);
+/* Page-locked host buffers for results (optional): device->host copies into them run at full PCIe speed instead
+ * of being staged through the driver (numpy arrays of the Python layer are allocated with these). */
+void* nbd_host_alloc(size_t bytes);
+void nbd_host_free(void* p);
 
 /* ---- multi-GPU plumbing -------------------------------------------------------------------- */
 /* NCCL communicator over the ranks that share one 3-centre tensor by auxiliary index.

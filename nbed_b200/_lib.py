@@ -16,7 +16,7 @@ NBD_MU_SHIFT = 1
 # every symbol include/nbed_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = [
     "nbd_version", "nbd_create", "nbd_destroy", "nbd_last_error", "nbd_set_option", "nbd_timer_ms",
-    "nbd_launch_count", "nbd_comm_unique_id", "nbd_comm_init", "nbd_cderi_alloc", "nbd_cderi_upload",
+    "nbd_launch_count", "nbd_host_alloc", "nbd_host_free", "nbd_comm_unique_id", "nbd_comm_init", "nbd_cderi_alloc", "nbd_cderi_upload",
     "nbd_cderi_synth", "nbd_cderi_download", "nbd_jk", "nbd_jk_dm", "nbd_scf_setup", "nbd_huzinaga_scf",
     "nbd_mu_scf", "nbd_scf_bench_init", "nbd_scf_bench_iteration", "nbd_ao2mo", "nbd_one_body",
     "nbd_spinorb_from_spatial",
@@ -63,6 +63,8 @@ def load() -> C.CDLL:
         "nbd_set_option": (I, [P, C.c_char_p, L]),
         "nbd_timer_ms": (D, [P, C.c_char_p]),
         "nbd_launch_count": (L, [P]),
+        "nbd_host_alloc": (P, [C.c_size_t]),
+        "nbd_host_free": (None, [P]),
         "nbd_comm_unique_id": (I, [P]),
         "nbd_comm_init": (I, [P, P, I, I]),
         "nbd_cderi_alloc": (I, [P, I, I]),
@@ -94,6 +96,23 @@ def ptr(a):
         return None
     assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
     return a.ctypes.data_as(C.c_void_p)
+
+
+def pinned_empty(shape) -> np.ndarray:
+    """float64 array in page-locked host memory (freed when the array is garbage collected).  Falls back to a
+    pageable array only if the allocation itself fails (results are identical, the copy is slower)."""
+    import weakref
+
+    lib = load()
+    shape = tuple(int(x) for x in np.atleast_1d(shape))
+    n = int(np.prod(shape)) if shape else 1
+    p = lib.nbd_host_alloc(n * 8)
+    if not p:
+        return np.empty(shape)
+    buf = (C.c_double * n).from_address(p)
+    arr = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+    weakref.finalize(buf, lib.nbd_host_free, p)
+    return arr
 
 
 def f64(a) -> np.ndarray:

@@ -657,6 +657,18 @@ double nbd_timer_ms(nbd_ctx* c, const char* key) {
 
 long nbd_launch_count(nbd_ctx* c) { return c ? c->launches : -1; }
 
+void* nbd_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void nbd_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 // ---- NCCL ---------------------------------------------------------------------------------------
 int nbd_comm_unique_id(void* unique_id_128) {
   std::string why;
