@@ -100,8 +100,100 @@ struct XArgs {
   double* X;            // group-major: column i of aux row P lives at X + xbase[i] + P * xstride[i]  (n_ld doubles)
   const long* xbase;    // [Ntot]
   const long* xstride;  // [Ntot]
+  const uint32_t* events;  // per-warp task lists (PanelPlan)
+  const int* evbegin;      // [9] offsets of the 8 consumer warps' lists; [9..16] = first tile index of each list
   int naux, ntiles, nb, n_ld, Ntot, nslices, nstages, ncolmax;
 };
+
+// ---------------------------------------------------------------------------------------------------
+// Per-warp task lists of the panel kernel.  An event = one tile a consumer warp takes part in:
+//   bits 0-7 I, 8-15 J, 16-20 distance (in tiles, cyclic over the row) to this warp's next event,
+//   21-25 weight of its arrival on the stage's "empty" barrier, 26 row task, 27 column task.
+// A warp only touches tiles it has an event on.  mbarrier parity waits can only tell the current phase from
+// the previous one, so two invariants are built into the lists: (1) consecutive events of a warp are at most
+// S tiles apart (dummy events - wait + release, no math - are inserted where a warp owns nothing for longer),
+// which together with 2S "full" barriers over S data stages guarantees a waiter is never two phases off;
+// (2) every tile's participants' weights add up to XK_EMPTY_COUNT, so a stage is refilled only after all of
+// them have released it.
+// ---------------------------------------------------------------------------------------------------
+constexpr int XK_EMPTY_COUNT = 16;
+struct PanelPlan {
+  int nb = 0, S = 0;
+  std::vector<uint32_t> events;
+  std::vector<int> begin;  // 9 offsets + 8 first-tile indices
+};
+inline PanelPlan build_panel_plan(int nb, int S, const std::vector<int>& seq) {
+  PanelPlan pl;
+  pl.nb = nb;
+  pl.S = S;
+  const int nt = (int)seq.size();
+  std::vector<std::vector<int>> ks(8);          // tile indices with an event, per warp
+  std::vector<std::vector<int>> flags(8);       // bit0 row, bit1 col (0 = dummy)
+  for (int w = 0; w < 8; ++w) {
+    std::vector<int> rk, rf;
+    for (int k = 0; k < nt; ++k) {
+      const int I = seq[k] >> 16, J = seq[k] & 0xffff;
+      const int f = (((I & 7) == w) ? 1 : 0) | ((((J & 7) == w) && I != J) ? 2 : 0);
+      if (f) {
+        rk.push_back(k);
+        rf.push_back(f);
+      }
+    }
+    if (rk.empty()) continue;
+    // dummies: first event within the first S tiles, consecutive gaps <= S, cyclic gap <= S
+    int prev = -1;
+    for (size_t e = 0; e < rk.size(); ++e) {
+      while (rk[e] - prev > S) {
+        prev += S;
+        ks[w].push_back(prev);
+        flags[w].push_back(0);
+      }
+      ks[w].push_back(rk[e]);
+      flags[w].push_back(rf[e]);
+      prev = rk[e];
+    }
+    while (nt - prev + ks[w][0] > S) {
+      prev = prev + S < nt - 1 ? prev + S : nt - 1;
+      ks[w].push_back(prev);
+      flags[w].push_back(0);
+    }
+  }
+  std::vector<int> npart(nt, 0), seen(nt, 0);
+  for (int w = 0; w < 8; ++w)
+    for (int k : ks[w]) ++npart[k];
+  pl.begin.assign(17, 0);
+  for (int w = 0; w < 8; ++w) {
+    pl.begin[w] = (int)pl.events.size();
+    pl.begin[9 + w] = ks[w].empty() ? 0 : ks[w][0];
+    const int ne = (int)ks[w].size();
+    for (int e = 0; e < ne; ++e) {
+      const int k = ks[w][e];
+      const int gap = e + 1 < ne ? ks[w][e + 1] - k : nt - k + ks[w][0];
+      const int weight = seen[k]++ == 0 ? XK_EMPTY_COUNT - (npart[k] - 1) : 1;
+      const int I = seq[k] >> 16, J = seq[k] & 0xffff;
+      pl.events.push_back((uint32_t)I | ((uint32_t)J << 8) | ((uint32_t)gap << 16) | ((uint32_t)weight << 21) |
+                          ((uint32_t)flags[w][e] << 26));
+    }
+  }
+  pl.begin[8] = (int)pl.events.size();
+  // self-check of the two invariants (cheap; a violated invariant would be a device-side hang)
+  std::vector<int> wsum(nt, 0);
+  for (int w = 0; w < 8; ++w) {
+    int k = pl.begin[9 + w];
+    if (pl.begin[w] < pl.begin[w + 1] && k > S - 1) pl.S = -1;
+    for (int e = pl.begin[w]; e < pl.begin[w + 1]; ++e) {
+      const uint32_t ev = pl.events[e];
+      const int gap = (ev >> 16) & 31;
+      if (gap < 1 || gap > S || (int)(ev & 255) != (seq[k] >> 16) || (int)((ev >> 8) & 255) != (seq[k] & 0xffff)) pl.S = -1;
+      wsum[k] += (ev >> 21) & 31;
+      k = (k + gap) % nt;
+    }
+    if (pl.begin[w] < pl.begin[w + 1] && k != pl.begin[9 + w]) pl.S = -1;
+  }
+  for (int k = 0; k < nt; ++k)
+    if (wsum[k] != XK_EMPTY_COUNT) pl.S = -1;
+  return pl;
+}
 
 // 8 consumer warps (warpgroups 0-1) + one producer warpgroup.  Registers are re-balanced with setmaxnreg
 // (the accumulators of a 1376-AO row set need ~200 registers per consumer thread; a 9-warp CTA would be
@@ -154,25 +246,21 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
   extern __shared__ __align__(128) unsigned char xsm[];
   constexpr int NCOL = 8 * NB;
   const int S = p.nstages;
-  uint64_t* full = reinterpret_cast<uint64_t*>(xsm);
-  uint64_t* empty = full + 16;
+  uint64_t* full = reinterpret_cast<uint64_t*>(xsm);  // 2S "full" barriers (tile q uses q mod 2S) ...
+  uint64_t* empty = full + 32;                        // ... over S data stages / "empty" barriers (q mod S)
   const int ct_ld = p.n_ld + 4;
   const int slice = blockIdx.x % p.nslices;
   const int col0 = slice * NCOL;
   const int ncol = min(NCOL, p.Ntot - col0);
-  // layout: [256 B barriers][tile sequence][(ncolmax + 1) rows of Ct][S stage buffers]   (sizes fixed by the host)
-  int* sseq = reinterpret_cast<int*>(xsm + 256);
-  const size_t seq_bytes = ((size_t)p.ntiles * 4 + 127) & ~(size_t)127;
-  double* cts = reinterpret_cast<double*>(xsm + 256 + seq_bytes);
+  // layout: [512 B barriers][(ncolmax + 1) rows of Ct][S stage buffers]   (sizes fixed by the host)
+  double* cts = reinterpret_cast<double*>(xsm + 512);
   const size_t ct_bytes = ((size_t)(p.ncolmax + 1) * ct_ld * 8 + 127) & ~(size_t)127;
-  double* stages = reinterpret_cast<double*>(xsm + 256 + seq_bytes + ct_bytes);
+  double* stages = reinterpret_cast<double*>(xsm + 512 + ct_bytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], XK_CONSUMER_WARPS);
-    }
+    for (int s = 0; s < 2 * S; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < S; ++s) mbar_init(&empty[s], XK_EMPTY_COUNT);
     mbar_fence_init();
   }
   __syncthreads();
@@ -184,7 +272,7 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
     // ===== producer warpgroup: one lane streams the tiles of every item of this CTA through the ring =====
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(XK_PRODUCER_REGS));
     if (warp == XK_CONSUMER_WARPS && lane == 0) {
-      int st = 0;
+      int st = 0, fb = 0;
       uint32_t ph = 1;  // parity of the "previous round released" phase; the first round needs no wait
       bool first_round = true;
       for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -192,8 +280,9 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
         const double* src = p.Bt + P * (long)p.ntiles * TILE_ELEMS;
         for (int k = 0; k < p.ntiles; ++k) {
           if (!first_round) mbar_wait(&empty[st], ph);
-          mbar_expect_tx(&full[st], TILE_BYTES);
-          bulk_g2s(stages + (size_t)st * TILE_ELEMS, src + (long)k * TILE_ELEMS, TILE_BYTES, &full[st]);
+          mbar_expect_tx(&full[fb], TILE_BYTES);
+          bulk_g2s(stages + (size_t)st * TILE_ELEMS, src + (long)k * TILE_ELEMS, TILE_BYTES, &full[fb]);
+          if (++fb == 2 * S) fb = 0;
           if (++st == S) {
             st = 0;
             ph ^= 1u;
@@ -216,7 +305,6 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
       for (int m = tid; m < p.n_ld; m += XK_CONSUMER_WARPS * 32) dst[m] = 0.0;
     }
   }
-  for (int k = tid; k < p.ntiles; k += XK_CONSUMER_WARPS * 32) sseq[k] = p.seq[k];
   asm volatile("bar.sync 1, %0;" ::"r"(XK_CONSUMER_WARPS * 32) : "memory");
 
   const int gq = lane >> 2, tq = lane & 3;
@@ -237,39 +325,42 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
 #pragma unroll
       for (int ni = 0; ni < NB; ++ni) X[s][mi][ni][0] = X[s][mi][ni][1] = 0.0;
 
-  int st = 0;
-  uint32_t ph = 0;
+  const int e0 = __ldg(p.evbegin + warp), e1 = __ldg(p.evbegin + warp + 1);
+  if (e0 == e1) return;  // this warp owns no panel of this matrix size: nothing to compute, wait for or write
+  const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+  const uint32_t stages_a = smem_u32(stages);
+  (void)stages_a;
+  uint32_t fb = (uint32_t)__ldg(p.evbegin + 9 + warp), par = 0;  // first event lies within the first S tiles
+  uint32_t ev_next = __ldg(p.events + e0);
   for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
     const long P = item / p.nslices;
-    for (int k = 0; k < p.ntiles; ++k) {
-      const int ij = sseq[k];
-      const int I = ij >> 16, J = ij & 0xffff;
-      const bool do_row = (I & 7) == warp;
-      const bool do_col = ((J & 7) == warp) && (I != J);
-      // Every consumer warp waits on, and releases, every tile - also those it has no task on.  A parity wait
-      // only tells the current phase from the previous one, so all waiters must stay within one round of a
-      // stage; gating the refill on all 8 warps guarantees that (and costs two shared-memory ops per tile).
-      mbar_wait(&full[st], ph);
-      if (do_row || do_col) {
+    for (int e = e0; e < e1; ++e) {
+      const uint32_t ev = ev_next;
+      ev_next = __ldg(p.events + (e + 1 < e1 ? e + 1 : e0));
+      const int I = ev & 255, J = (ev >> 8) & 255;
+      const uint32_t st = fb >= (uint32_t)S ? fb - (uint32_t)S : fb;
+      mbar_wait_a(full_a + 8u * fb, par);
+      if (ev & (3u << 26)) {
         const double* tile = stages + (size_t)st * TILE_ELEMS;
-        if (do_row) {
+        if (ev & (1u << 26)) {
           const int slot = I >> 3;
 #pragma unroll
           for (int s = 0; s < NSLOT; ++s)
             if (slot == s) xk_task_row<NB>(X[s], tile, crow, 32 * J, gq, tq, xoff);
         }
-        if (do_col) {
+        if (ev & (2u << 26)) {
           const int slot = J >> 3;
 #pragma unroll
           for (int s = 0; s < NSLOT; ++s)
             if (slot == s) xk_task_col<NB>(X[s], tile, crow, 32 * I, tq, yoff);
         }
+        __syncwarp();
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[st]);
-      if (++st == S) {
-        st = 0;
-        ph ^= 1u;
+      if (lane == 0) mbar_arrive_a(empty_a + 8u * st, (ev >> 21) & 31u);
+      fb += (ev >> 16) & 31u;
+      if (fb >= 2u * (uint32_t)S) {
+        fb -= 2u * (uint32_t)S;
+        par ^= 1u;
       }
     }
     // write this warp's panels of X[P] (group-major layout) and reset the accumulators

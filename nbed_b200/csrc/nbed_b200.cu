@@ -190,7 +190,8 @@ struct nbd_ctx {
   cusolverDnHandle_t solver2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int overlap = 1;
-  int dist_eig = 1;  // distribute the two spins' eigensolves over ranks 0 / 1 when a communicator exists
+  int dist_eig = 1;
+  int panel_stages = 0;  // tuning: cap on the ring depth of the panel kernel (0 = as many as fit)  // distribute the two spins' eigensolves over ranks 0 / 1 when a communicator exists
   std::string err;
   long launches = 0;
   StageTimers timers;
@@ -215,6 +216,9 @@ struct nbd_ctx {
   // ---- J/K workspaces ----
   DBuf<double> d_orb, d_wt, d_X, d_rho, d_jpart, d_jk;  // d_jk = [J sets | K sets] contiguous (all-reduce buffer)
   DBuf<int> d_setbegin;
+  PanelPlan plan;
+  DBuf<uint32_t> d_events;
+  DBuf<int> d_evbegin;
   DBuf<long> d_xtab;  // group-major layout tables of the half-transformed tensor: [xbase | xstride]
 
   // ---- SCF problem ----
@@ -347,18 +351,28 @@ static void half_transform(nbd_ctx* c, int p0, int np, const double* d_orb, int 
   }
   const int nslot = (c->nb + 7) / 8;
   NBD_REQUIRE(nslot <= 12, NBD_ERR_UNSUPPORTED, "nao = %d exceeds the 3072-AO envelope of the panel kernel", c->nao);
-  const size_t seq_bytes = ((size_t)c->ntiles * 4 + 127) & ~(size_t)127;
   auto smem_for = [&](int ncolmax, int stages) {
     const size_t ct = (((size_t)(ncolmax + 1) * (c->n_ld + 4) * 8) + 127) & ~(size_t)127;
-    return (size_t)256 + seq_bytes + ct + (size_t)stages * TILE_BYTES;
+    return (size_t)512 + ct + (size_t)stages * TILE_BYTES;
   };
   int NBsel = (Ntot > 8 && nslot <= 6) ? 2 : 1;
   if (NBsel == 2 && smem_for(std::min(16, Ntot), 6) > c->smem_optin) NBsel = 1;
   const int ncolmax = std::min(8 * NBsel, Ntot);
   NBD_REQUIRE(smem_for(ncolmax, 2) <= c->smem_optin, NBD_ERR_UNSUPPORTED, "nao = %d: orbital slice does not fit shared memory", c->nao);
-  int stages = 16;
+  int stages = c->panel_stages > 0 ? std::min(16, std::max(2, c->panel_stages)) : 16;
   while (stages > 2 && smem_for(ncolmax, stages) > c->smem_optin) --stages;
+  if (c->plan.nb != c->nb || c->plan.S != stages) {  // per-warp task lists for this (matrix size, ring depth)
+    c->plan = build_panel_plan(c->nb, stages, c->seq);
+    NBD_REQUIRE(c->plan.S == stages, NBD_ERR_STATE, "panel task lists failed their self-check (nb = %d, stages = %d)", c->nb, stages);
+    uint32_t* de = c->d_events.ensure(std::max<size_t>(1, c->plan.events.size()));
+    int* db = c->d_evbegin.ensure(17);
+    NBD_CUDA(cudaMemcpyAsync(de, c->plan.events.data(), sizeof(uint32_t) * c->plan.events.size(), cudaMemcpyHostToDevice, c->stream));
+    NBD_CUDA(cudaMemcpyAsync(db, c->plan.begin.data(), sizeof(int) * 17, cudaMemcpyHostToDevice, c->stream));
+    NBD_CUDA(cudaStreamSynchronize(c->stream));
+  }
   XArgs a{};
+  a.events = c->d_events.p;
+  a.evbegin = c->d_evbegin.p;
   a.Bt = c->Bt + (long)p0 * c->ntiles * TILE_ELEMS;
   a.seq = c->d_seq.p;
   a.Ct = d_orb;
@@ -457,14 +471,8 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
       rho_kernel<<<np, 256, 0, c->stream>>>(X, c->d_xtab.p, c->d_xtab.p + Ntot, d_wt, rho + p0, naux, n_ld, njset, c->d_setbegin.p);
       LAUNCH_CHECK(c);
     }
-    if (d_J && last && d_K && c->overlap) {
-      // pass 2 (HBM-bound) runs on the side stream next to the tensor-bound K Gram of this chunk
-      NBD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
-      NBD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-      j_pass(c->stream2);
-      NBD_CUDA(cudaEventRecord(c->ev_join, c->stream2));
-      forked = true;
-    }
+    const bool fork = d_J && last && d_K && c->overlap;
+    if (fork) NBD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
     if (d_K) {
       StageScope ts(c->timers, c->stream, "jk_k");
       // K_s (+)= alpha * X_g^T X_g with X_g the dense [np * w][n_ld] matrix of group g; consecutive groups of
@@ -487,6 +495,15 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
         }
         gi = gj;
       }
+    }
+    if (fork) {
+      // pass 2 (HBM-bound, no tensor work) runs on the side stream next to the tensor-bound K Gram of this chunk;
+      // it is launched AFTER the Gram so that the Gram's CTAs (one per SM, 135 KB of shared memory) are placed
+      // first and the streaming blocks fill the remaining thread slots
+      NBD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+      j_pass(c->stream2);
+      NBD_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+      forked = true;
     }
   }
   if (d_J && !forked) j_pass(c->stream);
@@ -645,6 +662,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "timers") c->timers.enabled = value != 0;
   else if (k == "overlap") c->overlap = (int)value;
   else if (k == "dist_eig") c->dist_eig = (int)value;
+  else if (k == "panel_stages") c->panel_stages = (int)value;
   else return NBD_ERR_ARG;
   return NBD_OK;
 }
@@ -710,6 +728,7 @@ int nbd_cderi_alloc(nbd_ctx* c, int nao, int naux_local) {
     c->npair = (long)nao * (nao + 1) / 2;
     c->naux = naux_local;
     c->seq = build_tile_sequence(c->nb);
+    c->plan = PanelPlan();
     NBD_REQUIRE((int)c->seq.size() == c->ntiles, NBD_ERR_STATE, "tile sequence has %zu entries, expected %d", c->seq.size(), c->ntiles);
     c->inv.assign((size_t)c->nb * c->nb, -1);
     for (int k = 0; k < c->ntiles; ++k) c->inv[(size_t)(c->seq[k] >> 16) * c->nb + (c->seq[k] & 0xffff)] = k;

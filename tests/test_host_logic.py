@@ -99,3 +99,13 @@ def test_bench_reference_arm_emits_contract_line():
         assert key in line, key
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_panel_task_lists_keep_their_ring_invariants(tmp_path):
+    """Host-side check of the panel kernel's per-warp event lists for every matrix size / ring depth: consecutive
+    events of a warp at most S tiles apart (cyclically), arrival weights of every tile summing to the barrier count."""
+    exe = tmp_path / "plan_test"
+    src = os.path.join(ROOT, "tests", "cpp", "plan_test.cu")
+    subprocess.run(["nvcc", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", str(exe), src], check=True, timeout=300)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout[-500:]
