@@ -33,6 +33,12 @@ def unpack_tril(p: np.ndarray, n: int | None = None) -> np.ndarray:
     npair = p.shape[-1]
     if n is None:
         n = int((np.sqrt(8 * npair + 1) - 1) // 2)
+    if p.ndim >= 2 and p.size >= 1 << 16:  # large blocks: C helper (what pyscf.lib.unpack_tril is), if built
+        from . import c_binding
+
+        out = c_binding.unpack_tril(p, n)
+        if out is not None:
+            return out
     out = np.zeros(p.shape[:-1] + (n, n))
     il = np.tril_indices(n)
     out[..., il[0], il[1]] = p
@@ -90,8 +96,9 @@ def df_get_jk(cderi: np.ndarray, dm, with_j=True, with_k=True, blksize: int = 24
             for k in range(nset):
                 if orbo is not None:
                     if orbo[k].shape[1] > 0:
-                        buf1 = np.einsum("pmn,ni->pim", b, orbo[k], optimize=True).reshape(-1, nao)
-                        vk[k] += buf1.T @ buf1
+                        buf1 = (b.reshape(-1, nao) @ orbo[k]).reshape(b.shape[0], nao, -1)  # [p, m, i]
+                        buf1 = np.ascontiguousarray(buf1.transpose(1, 0, 2)).reshape(nao, -1)  # [m, (p, i)]
+                        vk[k] += buf1 @ buf1.T
                 else:
                     buf1 = np.einsum("pmn,nl->pml", b, dms[k], optimize=True)
                     vk[k] += np.einsum("pml,pln->mn", buf1, b, optimize=True)

@@ -116,3 +116,20 @@ def test_oracle_jk_dense_and_orbital_branches_agree():
     dm = np.array([o @ o.T for o in orbs])
     assert np.abs(vj - np.einsum("ijkl,skl->sij", eri, dm)).max() < 1e-12
     assert np.abs(vk - np.einsum("ikjl,skl->sij", eri, dm)).max() < 1e-12
+
+
+def test_c_restatement_agrees_with_numpy_restatement():
+    """oracle/c_kernels.c (plain C, built by oracle/Makefile) against the NumPy restatement of df_jk.get_jk."""
+    from oracle import c_binding
+
+    if c_binding.load() is None:
+        pytest.skip("C oracle could not be built (no gcc with OpenMP)")
+    p, b = scf_problem("C2_h2o_ccpvdz", 3.0)
+    rng = np.random.default_rng(3)
+    orbs = [rng.normal(size=(p.n, 4)), rng.normal(size=(p.n, 0)), rng.normal(size=(p.n, 7))]
+    vj, vk = c_binding.df_jk_occ(b, orbs)
+    rj, rk = ps.df_get_jk_occ(b, orbs)
+    assert np.abs(vj - rj).max() < 1e-13 and np.abs(vk - rk).max() < 1e-13
+    full = c_binding.unpack_tril(b, p.n)
+    il = np.tril_indices(p.n)
+    assert np.array_equal(full[:, il[0], il[1]], b) and np.array_equal(full, full.transpose(0, 2, 1))
