@@ -16,6 +16,7 @@
 #include "host_util.cuh"
 #include "jk.cuh"
 #include "scf_kernels.cuh"
+#include "subspace.cuh"
 
 using namespace nbd;
 
@@ -230,6 +231,15 @@ struct nbd_ctx {
       Corth, Ssave, dm0f;
   DBuf<int> devinfo;
   DiisState diis;
+  // subspace (Chebyshev-filtered) tracking of the occupied block between full eigensolves
+  int eig_mode = 1;  // 0: cuSOLVER every cycle; 1: filtered subspace iteration when eligible (cuSOLVER first / last / fallback)
+  bool sub_valid = false;
+  bool last_eig_full = true;
+  int sub_kb = 0;
+  long sub_applies = 0, sub_fallbacks = 0, sub_outer = 0;
+  double sub_theta[2][32];
+  DBuf<double> sV, sY, sZ, sW, sAV, sPart, sG, sGpart, sM, sTheta, sRpart, sBound;
+  DBuf<unsigned int> sTicket;
   // bench state
   bool bench_ready = false;
   double bench_eprev[2] = {0, 0};
@@ -663,12 +673,17 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "overlap") c->overlap = (int)value;
   else if (k == "dist_eig") c->dist_eig = (int)value;
   else if (k == "panel_stages") c->panel_stages = (int)value;
+  else if (k == "eig_mode") { c->eig_mode = (int)value; c->sub_valid = false; }
   else return NBD_ERR_ARG;
   return NBD_OK;
 }
 
 double nbd_timer_ms(nbd_ctx* c, const char* key) {
   if (!c || !key) return -1.0;
+  // cumulative counters of the subspace eigensolver (since context creation)
+  if (!strcmp(key, "count:sub_applies")) return (double)c->sub_applies;
+  if (!strcmp(key, "count:sub_outer")) return (double)c->sub_outer;
+  if (!strcmp(key, "count:sub_fallbacks")) return (double)c->sub_fallbacks;
   auto it = c->timers.ms.find(key);
   return it == c->timers.ms.end() ? 0.0 : it->second;
 }
@@ -945,5 +960,6 @@ extern "C" int nbd_jk_dm(nbd_ctx* c, int nset, const double* dm, double* vj, dou
   });
 }
 
+#include "subspace_host.cuh"
 #include "scf_host.cuh"
 #include "ao2mo_host.cuh"

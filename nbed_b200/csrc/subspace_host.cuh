@@ -1,0 +1,219 @@
+// Host driver of the Chebyshev-filtered subspace iteration (subspace.cuh).  Included by nbed_b200.cu before
+// scf_host.cuh.
+#pragma once
+
+static int sub_block_size(const nbd_ctx* c) {
+  int omax = 0;
+  for (int s = 0; s < c->nspin; ++s) omax = std::max(omax, c->nspin == 2 ? c->nelec[s] : (c->nelec[0] + c->nelec[1]) / 2);
+  if (c->eig_mode != 1 || c->projector != NBD_HUZINAGA || c->nao < 256 || omax < 1) return 0;
+  if (omax <= 10) return 16;
+  if (omax <= 24) return 32;
+  return 0;
+}
+
+static void sub_alloc(nbd_ctx* c, int kb) {
+  const size_t blk = (size_t)2 * c->nao * kb;
+  for (DBuf<double>* b : {&c->sV, &c->sY, &c->sZ, &c->sW, &c->sAV}) b->ensure(blk);
+  c->sPart.ensure(blk * SUB_MAX_SPLIT);
+  c->sG.ensure((size_t)2 * 2 * kb * kb);
+  c->sGpart.ensure((size_t)2 * 64 * 2 * kb * kb);
+  c->sM.ensure((size_t)2 * kb * kb);
+  c->sTheta.ensure((size_t)2 * kb);
+  c->sRpart.ensure((size_t)2 * 64 * kb);
+  c->sBound.ensure(8);
+  if (c->sTicket.cap < 4096) {
+    c->sTicket.ensure(4096);
+    NBD_CUDA(cudaMemsetAsync(c->sTicket.p, 0, sizeof(unsigned int) * 4096, c->stream));
+  }
+}
+
+// after a full eigensolve: rows of `eigrows` ([nspin][n][n], row = eigenvector, ascending) -> tracked block
+static void sub_init_from_full(nbd_ctx* c, const double* eigrows, const double* evals_dev) {
+  const int kb = sub_block_size(c);
+  c->sub_valid = false;
+  if (!kb) return;
+  const int n = c->nao;
+  sub_alloc(c, kb);
+  dim3 g((n + 127) / 128, kb, c->nspin);
+  sub_gather_block_kernel<<<g, 128, 0, c->stream>>>(eigrows, c->sV.p, n, kb, (long)n * n, (long)n * kb);
+  LAUNCH_CHECK(c);
+  std::vector<double> w((size_t)c->nspin * n);
+  d2h(c, w.data(), evals_dev, (size_t)c->nspin * n);
+  NBD_CUDA(cudaStreamSynchronize(c->stream));
+  for (int s = 0; s < c->nspin; ++s)
+    for (int k = 0; k < kb; ++k) c->sub_theta[s][k] = w[(size_t)s * n + k];
+  c->sub_kb = kb;
+  c->sub_valid = true;
+}
+
+template <int KB>
+static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double* Z, double* out, const double* alpha,
+                      const double* shift, const double* beta) {
+  const int n = c->nao;
+  SubApplyArgs a{};
+  a.A = A; a.Y = Y; a.Z = Z; a.out = out; a.part = c->sPart.p; a.ticket = c->sTicket.p;
+  a.n = n;
+  const int nrb = (n + SUB_ROWS - 1) / SUB_ROWS;
+  // latency-bound kernel over L2-resident data: many short CTAs (about 4-5 per SM) beat few long ones
+  a.nsplit = std::max(1, std::min(SUB_MAX_SPLIT, (5 * c->sm_count) / std::max(1, nrb * c->nspin)));
+  for (int b = 0; b < 2; ++b) {
+    a.alpha[b] = alpha[b]; a.shift[b] = shift[b]; a.beta[b] = beta[b];
+  }
+  dim3 g(nrb, a.nsplit, c->nspin);
+  sub_apply_kernel<KB><<<g, 256, 0, c->stream>>>(a);
+  LAUNCH_CHECK(c);
+  ++c->sub_applies;
+}
+
+// host: orthonormalise + Rayleigh-Ritz.  G = Y^T Y, H = Y^T A Y  ->  M (Y M orthonormal Ritz vectors), theta ascending
+static bool sub_rayleigh_ritz(int kb, const double* G, const double* H, double* M, double* theta) {
+  std::vector<double> d(kb), gs((size_t)kb * kb), hs((size_t)kb * kb), L((size_t)kb * kb, 0.0), Li((size_t)kb * kb, 0.0);
+  for (int i = 0; i < kb; ++i) {
+    if (!(G[(size_t)i * kb + i] > 0.0)) return false;
+    d[i] = 1.0 / std::sqrt(G[(size_t)i * kb + i]);
+  }
+  for (int i = 0; i < kb; ++i)
+    for (int j = 0; j < kb; ++j) {
+      gs[(size_t)i * kb + j] = 0.5 * (G[(size_t)i * kb + j] + G[(size_t)j * kb + i]) * d[i] * d[j];
+      hs[(size_t)i * kb + j] = 0.5 * (H[(size_t)i * kb + j] + H[(size_t)j * kb + i]) * d[i] * d[j];
+    }
+  for (int j = 0; j < kb; ++j) {  // Cholesky gs = L L^T
+    double s = gs[(size_t)j * kb + j];
+    for (int k = 0; k < j; ++k) s -= L[(size_t)j * kb + k] * L[(size_t)j * kb + k];
+    if (!(s > 1e-12)) return false;  // (columns are normalised: a tiny pivot means a numerically dependent block)
+    L[(size_t)j * kb + j] = std::sqrt(s);
+    for (int i = j + 1; i < kb; ++i) {
+      double t = gs[(size_t)i * kb + j];
+      for (int k = 0; k < j; ++k) t -= L[(size_t)i * kb + k] * L[(size_t)j * kb + k];
+      L[(size_t)i * kb + j] = t / L[(size_t)j * kb + j];
+    }
+  }
+  for (int j = 0; j < kb; ++j) {  // Li = L^-1 (lower)
+    Li[(size_t)j * kb + j] = 1.0 / L[(size_t)j * kb + j];
+    for (int i = j + 1; i < kb; ++i) {
+      double t = 0.0;
+      for (int k = j; k < i; ++k) t -= L[(size_t)i * kb + k] * Li[(size_t)k * kb + j];
+      Li[(size_t)i * kb + j] = t / L[(size_t)i * kb + i];
+    }
+  }
+  std::vector<double> t1((size_t)kb * kb, 0.0), ht((size_t)kb * kb, 0.0), w, q;
+  for (int i = 0; i < kb; ++i)  // t1 = Li hs
+    for (int j = 0; j < kb; ++j) {
+      double t = 0.0;
+      for (int k = 0; k <= i; ++k) t += Li[(size_t)i * kb + k] * hs[(size_t)k * kb + j];
+      t1[(size_t)i * kb + j] = t;
+    }
+  for (int i = 0; i < kb; ++i)  // ht = t1 Li^T
+    for (int j = 0; j < kb; ++j) {
+      double t = 0.0;
+      for (int k = 0; k <= j; ++k) t += t1[(size_t)i * kb + k] * Li[(size_t)j * kb + k];
+      ht[(size_t)i * kb + j] = t;
+    }
+  for (int i = 0; i < kb; ++i)
+    for (int j = 0; j < i; ++j) ht[(size_t)i * kb + j] = ht[(size_t)j * kb + i] = 0.5 * (ht[(size_t)i * kb + j] + ht[(size_t)j * kb + i]);
+  jacobi_eigh(kb, ht, w, q);  // columns of q = eigenvectors
+  std::vector<int> order(kb);
+  for (int i = 0; i < kb; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return w[a] < w[b]; });
+  for (int c = 0; c < kb; ++c) {
+    theta[c] = w[order[c]];
+    for (int i = 0; i < kb; ++i) {  // M[i][c] = d_i * sum_k Li[k][i] q[k][order c]
+      double t = 0.0;
+      for (int k = i; k < kb; ++k) t += Li[(size_t)k * kb + i] * q[(size_t)k * kb + order[c]];
+      M[(size_t)i * kb + c] = d[i] * t;
+    }
+  }
+  return true;
+}
+
+// Tracks the KB lowest eigenvectors of Fp ([nspin][n][n], Lowdin basis) starting from c->sV.
+// On success c->sV holds the Ritz vectors, c->sub_theta the Ritz values; returns false when it did not converge.
+template <int KB>
+static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
+  const int n = c->nao, ns = c->nspin;
+  const long blk = (long)n * KB;
+  constexpr int NBLK = 64;
+  const int degree = 24, max_outer = 14;
+  const double tol = 1e-10;
+  double bound[2] = {0, 0};
+  sub_gershgorin_kernel<<<ns, 1024, 0, c->stream>>>(Fp, n, c->sBound.p);
+  LAUNCH_CHECK(c);
+  d2h(c, bound, c->sBound.p, ns);
+  NBD_CUDA(cudaStreamSynchronize(c->stream));
+  const double one[2] = {1.0, 1.0}, zero[2] = {0.0, 0.0};
+  double* cur = c->sV.p;  // block to Rayleigh-Ritz next
+  for (int outer = 0; outer < max_outer; ++outer) {
+    if (outer > 0) {
+      // scaled Chebyshev filter of degree `degree` damping [a, bound] (Zhou & Saad), per spin
+      double e[2], cc[2], sig[2], sig1[2], al[2], be[2];
+      for (int s = 0; s < ns; ++s) {
+        const double a = c->sub_theta[s][KB - 1], a0 = c->sub_theta[s][0];
+        const double bu = std::max(bound[s], a + 1e-3) * 1.0000001 + 1e-9;
+        e[s] = 0.5 * (bu - a);
+        cc[s] = 0.5 * (bu + a);
+        sig1[s] = e[s] / (a0 - cc[s]);
+        sig[s] = sig1[s];
+        al[s] = sig1[s] / e[s];
+      }
+      sub_apply<KB>(c, Fp, c->sV.p, nullptr, c->sY.p, al, cc, zero);
+      double* prev = c->sV.p;
+      double* y = c->sY.p;
+      double* z = c->sZ.p;
+      for (int i = 2; i <= degree; ++i) {
+        for (int s = 0; s < ns; ++s) {
+          const double sig2 = 1.0 / (2.0 / sig1[s] - sig[s]);
+          al[s] = 2.0 * sig2 / e[s];
+          be[s] = sig[s] * sig2;
+          sig[s] = sig2;
+        }
+        sub_apply<KB>(c, Fp, y, prev, z, al, cc, be);
+        double* t = prev;
+        prev = y;
+        y = z;
+        z = t;
+      }
+      cur = y;
+    }
+    // W = F' Y ; G = Y^T Y, H = Y^T W ; host Rayleigh-Ritz ; V = Y M, AV = W M, residuals
+    sub_apply<KB>(c, Fp, cur, nullptr, c->sW.p, one, zero, zero);
+    sub_gram_kernel<KB><<<dim3(NBLK, ns), 256, 0, c->stream>>>(cur, c->sW.p, c->sGpart.p, c->sG.p, c->sTicket.p + 2048, n);
+    LAUNCH_CHECK(c);
+    std::vector<double> G((size_t)ns * 2 * KB * KB), M((size_t)ns * KB * KB), th((size_t)ns * KB);
+    d2h(c, G.data(), c->sG.p, G.size());
+    NBD_CUDA(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < ns; ++s)
+      if (!sub_rayleigh_ritz(KB, G.data() + (size_t)s * 2 * KB * KB, G.data() + (size_t)s * 2 * KB * KB + KB * KB,
+                             M.data() + (size_t)s * KB * KB, th.data() + (size_t)s * KB))
+        return false;
+    h2d(c, c->sM.p, M.data(), M.size());
+    h2d(c, c->sTheta.p, th.data(), th.size());
+    // rotate into a buffer that is not `cur` (cur may alias sV / sY / sZ): use sAV for A V and the free one for V
+    double* vout = (cur == c->sV.p) ? c->sY.p : c->sV.p;
+    sub_rotate_kernel<KB><<<dim3(NBLK, ns), 256, 0, c->stream>>>(cur, c->sW.p, c->sM.p, c->sTheta.p, vout, c->sAV.p, c->sRpart.p, n);
+    LAUNCH_CHECK(c);
+    if (vout != c->sV.p) NBD_CUDA(cudaMemcpyAsync(c->sV.p, vout, sizeof(double) * blk * ns, cudaMemcpyDeviceToDevice, c->stream));
+    std::vector<double> rp((size_t)ns * NBLK * KB);
+    d2h(c, rp.data(), c->sRpart.p, rp.size());
+    NBD_CUDA(cudaStreamSynchronize(c->stream));
+    double worst = 0.0;
+    for (int s = 0; s < ns; ++s) {
+      const int o = ns == 2 ? c->nelec[s] : (c->nelec[0] + c->nelec[1]) / 2;
+      for (int k = 0; k < KB; ++k) c->sub_theta[s][k] = th[(size_t)s * KB + k];
+      for (int k = 0; k < o; ++k) {
+        double r2 = 0.0;
+        for (int bl = 0; bl < NBLK; ++bl) r2 += rp[((size_t)s * NBLK + bl) * KB + k];
+        worst = std::max(worst, std::sqrt(r2));
+      }
+    }
+    ++c->sub_outer;
+    if (worst < tol) return true;
+  }
+  return false;
+}
+
+static bool sub_solve(nbd_ctx* c, const double* Fp) {
+  StageScope ts(c->timers, c->stream, "eig_sub");
+  if (c->sub_kb == 16) return sub_solve_t<16>(c, Fp);
+  if (c->sub_kb == 32) return sub_solve_t<32>(c, Fp);
+  return false;
+}

@@ -116,3 +116,39 @@ def test_mu_shift_iterates(ctx, name, scale, _plain, mu):
     assert np.abs(d1 - dref).max() < 1e-7
     assert np.array_equal(occ1, mf.mo_occ)
     assert np.abs(e1[:, : p.nocc] - mf.mo_energy[:, : p.nocc]).max() < 1e-6
+
+
+@pytest.mark.parametrize("n,naux,nocc,n_env,scale", [(300, 40, 5, 12, 4.0), (330, 24, 9, 20, 4.0), (272, 30, 14, 6, 3.0)])
+def test_huzinaga_subspace_eigensolver_matches_full_diagonalisation(ctx, n, naux, nocc, n_env, scale):
+    """n >= 256: between the first and the last cycle the occupied block is tracked by Chebyshev-filtered subspace
+    iteration instead of a full cuSOLVER solve.  Iterates must match both the oracle (full numpy
+    eigh every cycle, like the reference) and the library's own eig_mode = 0."""
+    p = syn.make_problem(n=n, naux=naux, nocc=nocc, n_env=n_env, seed=0, scale=scale / np.sqrt(n * naux))
+    b = p.cderi()
+    mf = ps.DFUHF(p.ovlp, p.hcore, b, p.nelec, max_cycle=30, conv_tol=1e-8)
+    tr = []
+    c0, e0, d0, h0, conv0 = nr.huzinaga_scf(mf, p.v_emb, p.dm_enviro, trace=tr)
+    assert len(tr) >= 5  # enough cycles for the subspace path to matter
+    ctx.load_cderi(b)
+    out = {}
+    for mode in (0, 1):
+        ctx.set_option("eig_mode", mode)
+        try:
+            ctx.scf_setup(p.nelec, p.ovlp, p.hcore, p.v_emb, p.dm_enviro, NBD_HUZINAGA)
+            applies0 = ctx.timer_ms("count:sub_applies")
+            out[mode] = ctx.huzinaga_scf(30, 1e-8, 1e-6, True)
+            used = ctx.timer_ms("count:sub_applies") - applies0
+        finally:
+            ctx.set_option("eig_mode", 1)
+        assert (used > 0) == (mode == 1)
+        c1, e1, d1, h1, info = out[mode]
+        _same_stop(info, conv0, tr)
+        for k, t in enumerate(tr[: info["cycles"]]):
+            assert np.abs(info["trace"][k, :2] - t["energy"]).max() < E_TOL, (mode, k)
+            assert abs(info["trace"][k, 2] - t["norm_dm_diff"]) < 1e-8, (mode, k)
+        assert np.abs(d1 - d0).max() < 1e-8 and np.abs(h1 - h0).max() < 1e-7
+        assert np.abs(e1 - e0).max() < 1e-8  # the FULL spectrum is returned in both modes
+        for s in range(2):
+            ov = np.abs(np.einsum("mi,mn,ni->i", c0[s], p.ovlp, c1[s]))
+            assert np.abs(ov[: p.nocc] - 1).max() < 1e-6
+    assert np.abs(out[0][2] - out[1][2]).max() < 1e-9
