@@ -71,10 +71,12 @@ static void jacobi_eigh(int n, std::vector<double> a, std::vector<double>& w, st
   v.assign((size_t)n * n, 0.0);
   for (int i = 0; i < n; ++i) v[(size_t)i * n + i] = 1.0;
   for (int sweep = 0; sweep < 100; ++sweep) {
-    double off = 0.0;
-    for (int p = 0; p < n; ++p)
+    double off = 0.0, diag = 0.0;
+    for (int p = 0; p < n; ++p) {
+      diag += a[(size_t)p * n + p] * a[(size_t)p * n + p];
       for (int q = p + 1; q < n; ++q) off += a[(size_t)p * n + q] * a[(size_t)p * n + q];
-    if (off < 1e-300) break;
+    }
+    if (off <= 1e-34 * (diag + 2.0 * off) || off < 1e-300) break;  // off-diagonal norm below 1e-17 of the matrix norm
     for (int p = 0; p < n; ++p)
       for (int q = p + 1; q < n; ++q) {
         const double apq = a[(size_t)p * n + q];

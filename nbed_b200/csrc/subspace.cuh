@@ -213,24 +213,23 @@ __global__ void __launch_bounds__(256) sub_rotate_kernel(const double* __restric
   }
 }
 
-// Gershgorin upper bound of the spectrum: out[b] = max_i sum_j |A[b][i][j]|   (one CTA per batch entry)
-__global__ void __launch_bounds__(1024) sub_gershgorin_kernel(const double* __restrict__ Aall, int n, double* __restrict__ out) {
-  __shared__ double red[32];
-  const double* A = Aall + (long)blockIdx.x * n * n;
-  double best = 0.0;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int i = warp; i < n; i += nw) {
-    double s = 0.0;
+// Gershgorin-type upper bound of the spectrum: part[b][blk] = max over the block's rows of sum_j |A[b][i][j]|
+// (the host takes the max over blocks); one warp per row, 8 rows per CTA.
+__global__ void __launch_bounds__(256) sub_gershgorin_kernel(const double* __restrict__ Aall, int n, double* __restrict__ part) {
+  __shared__ double red[8];
+  const double* A = Aall + (long)blockIdx.y * n * n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  double s = 0.0;
+  if (i < n)
     for (int j = lane; j < n; j += 32) s += fabs(A[(long)i * n + j]);
-    s = warp_sum(s);
-    best = fmax(best, s);
-  }
-  if (lane == 0) red[warp] = best;
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     double m = 0.0;
-    for (int w = 0; w < nw; ++w) m = fmax(m, red[w]);
-    out[blockIdx.x] = m;
+    for (int w = 0; w < 8; ++w) m = fmax(m, red[w]);
+    part[(long)blockIdx.y * gridDim.x + blockIdx.x] = m;
   }
 }
 

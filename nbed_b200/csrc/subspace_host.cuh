@@ -136,10 +136,17 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
   const int degree = 24, max_outer = 14;
   const double tol = 1e-10;
   double bound[2] = {0, 0};
-  sub_gershgorin_kernel<<<ns, 1024, 0, c->stream>>>(Fp, n, c->sBound.p);
-  LAUNCH_CHECK(c);
-  d2h(c, bound, c->sBound.p, ns);
-  NBD_CUDA(cudaStreamSynchronize(c->stream));
+  {
+    const int nblk = (n + 7) / 8;
+    double* bp = c->sBound.ensure((size_t)2 * nblk);
+    sub_gershgorin_kernel<<<dim3(nblk, ns), 256, 0, c->stream>>>(Fp, n, bp);
+    LAUNCH_CHECK(c);
+    std::vector<double> hb((size_t)ns * nblk);
+    d2h(c, hb.data(), bp, hb.size());
+    NBD_CUDA(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < ns; ++s)
+      for (int k = 0; k < nblk; ++k) bound[s] = std::max(bound[s], hb[(size_t)s * nblk + k]);
+  }
   const double one[2] = {1.0, 1.0}, zero[2] = {0.0, 0.0};
   double* cur = c->sV.p;  // block to Rayleigh-Ritz next
   for (int outer = 0; outer < max_outer; ++outer) {
