@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnbed_b200.so")
 SOURCES = ["nbed_b200.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "jk.cuh", "scf_kernels.cuh", "host_util.cuh", "scf_host.cuh", "ao2mo_host.cuh"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))  # every header the one TU includes
 
 
 def _nccl_include() -> str:
@@ -49,7 +49,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
         print(" ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
+    tmp = LIB + ".tmp"
+    cmd[cmd.index("-o") + 1] = tmp
+    subprocess.run(cmd, check=True)  # raises on any compile error; the old library is only replaced on success
+    os.replace(tmp, LIB)
     return LIB
 
 

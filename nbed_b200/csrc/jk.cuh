@@ -468,6 +468,96 @@ __global__ void __launch_bounds__(256) j_pass_kernel(const double2* __restrict__
   for (int s = 0; s < NSET; ++s) part[((long)split * NSET + s) * E2 + idx] = acc[s];
 }
 
+// TMA-fed variant of pass 2: persistent CTAs (a few per SM), a producer warp streams tile k of the aux rows of one
+// P-range through a ring of 8 KiB bulk copies, four consumer warps accumulate rho[P] * tile in registers.  It keeps
+// ~64 KiB in flight per CTA with 160 threads and 17 registers' worth of accumulators, so it reaches HBM speed next
+// to the tensor-bound K Gram (whose CTAs leave little room for the register-hungry LDG version above).
+constexpr int JP_STAGES = 8;
+constexpr int JP_THREADS = 160;  // 4 consumer warps + 1 producer warp
+template <int NSET>
+__global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __restrict__ Bt, const double* __restrict__ rho,
+                                                                double* __restrict__ part, int ntiles, int naux,
+                                                                int nsplit, int rows_per_split) {
+  extern __shared__ __align__(128) unsigned char jsm[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(jsm);
+  uint64_t* empty = full + JP_STAGES;
+  double* stages = reinterpret_cast<double*>(jsm + 128);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < JP_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 4);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const long nitems = (long)ntiles * nsplit;  // item = (split, tile): consecutive CTAs take consecutive tiles
+  if (warp == 4) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 1;
+      bool first = true;
+      for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int sp = (int)(item / ntiles), k = (int)(item % ntiles);
+        const int p0 = sp * rows_per_split, p1 = min(naux, p0 + rows_per_split);
+        const double* src = Bt + ((long)p0 * ntiles + k) * TILE_ELEMS;
+        for (int p = p0; p < p1; ++p, src += (long)ntiles * TILE_ELEMS) {
+          if (!first) mbar_wait(&empty[st], ph);
+          mbar_expect_tx(&full[st], TILE_BYTES);
+          bulk_g2s(stages + (size_t)st * TILE_ELEMS, src, TILE_BYTES, &full[st]);
+          if (++st == JP_STAGES) {
+            st = 0;
+            ph ^= 1u;
+            first = false;
+          }
+        }
+      }
+    }
+    return;
+  }
+  const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+  uint32_t st = 0, ph = 0;
+  for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int sp = (int)(item / ntiles), k = (int)(item % ntiles);
+    const int p0 = sp * rows_per_split, p1 = min(naux, p0 + rows_per_split);
+    double2 acc[NSET][4];
+#pragma unroll
+    for (int s = 0; s < NSET; ++s)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[s][q] = make_double2(0.0, 0.0);
+    for (int p = p0; p < p1; ++p) {
+      double r[NSET];
+#pragma unroll
+      for (int s = 0; s < NSET; ++s) r[s] = __ldg(rho + (long)s * naux + p);
+      mbar_wait_a(full_a + 8u * st, ph);
+      const double2* t2 = reinterpret_cast<const double2*>(stages + (size_t)st * TILE_ELEMS);
+      double2 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = t2[tid + 128 * q];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(empty_a + 8u * st);
+#pragma unroll
+      for (int s = 0; s < NSET; ++s)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[s][q].x = fma(r[s], v[q].x, acc[s][q].x);
+          acc[s][q].y = fma(r[s], v[q].y, acc[s][q].y);
+        }
+      if (++st == JP_STAGES) {
+        st = 0;
+        ph ^= 1u;
+      }
+    }
+    // part[split][set][tile k][1024]
+#pragma unroll
+    for (int s = 0; s < NSET; ++s) {
+      double2* o = reinterpret_cast<double2*>(part + (((long)sp * NSET + s) * ntiles + k) * TILE_ELEMS);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[tid + 128 * q] = acc[s][q];
+    }
+  }
+}
+
 // J[set][mu][nu] (square, symmetric) from the split partials in tiled layout
 __global__ void j_finalize_kernel(const double* __restrict__ part, const int* __restrict__ inv, double* __restrict__ J,
                                   int n, int nb, long E, int nsplit, int nset) {

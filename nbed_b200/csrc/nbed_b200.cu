@@ -194,6 +194,7 @@ struct nbd_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int overlap = 1;
   int dist_eig = 1;
+  int jpass_variant = 0;  // 0: TMA-fed persistent pass 2, 1: LDG streaming pass 2
   int panel_stages = 0;  // tuning: cap on the ring depth of the panel kernel (0 = as many as fit)  // distribute the two spins' eigensolves over ranks 0 / 1 when a communicator exists
   std::string err;
   long launches = 0;
@@ -451,6 +452,43 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
   auto j_pass = [&](cudaStream_t st) {
     StageScope ts(c->timers, st, "jk_j");
     const long E = (long)c->ntiles * TILE_ELEMS, E2 = E / 2;
+    dim3 gf((n + 127) / 128, n);
+    if (c->jpass_variant == 0) {
+      // TMA-fed persistent kernel: items = (P-range, tile); pick the split that balances the static round-robin
+      const int ctas = 2 * c->sm_count;
+      int nsplit = 1;
+      double best = 1e30;
+      for (int sp = 1; sp <= std::min(naux, 8); ++sp) {
+        const long items = (long)c->ntiles * sp;
+        const double rounds = std::ceil((double)items / ctas), cost = rounds / sp;  // time ~ rounds * rows per item
+        if (cost < best * 0.999) {
+          best = cost;
+          nsplit = sp;
+        }
+      }
+      const int rows_per_split = (naux + nsplit - 1) / nsplit;
+      nsplit = (naux + rows_per_split - 1) / rows_per_split;
+      const size_t smem = 128 + (size_t)JP_STAGES * TILE_BYTES;
+      static bool attr_set = false;
+      if (!attr_set) {
+        NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      for (int s0 = 0; s0 < njset; s0 += 2) {
+        const int ns = std::min(2, njset - s0);
+        double* part = c->d_jpart.ensure((size_t)nsplit * ns * E);
+        const int grid = (int)std::min<long>((long)c->ntiles * nsplit, ctas);
+        if (ns == 2)
+          j_pass_tma_kernel<2><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split);
+        else
+          j_pass_tma_kernel<1><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split);
+        LAUNCH_CHECK(c);
+        j_finalize_kernel<<<gf, 128, 0, st>>>(part, c->d_inv.p, d_J + (long)s0 * nn, n, c->nb, E, nsplit, ns);
+        LAUNCH_CHECK(c);
+      }
+      return;
+    }
     const int bx = (int)((E2 + 255) / 256);
     int nsplit = (int)std::min<long>(std::min(naux, 64), std::max<long>(1, ((long)c->sm_count * 16 + bx - 1) / bx));
     const int rows_per_split = (naux + nsplit - 1) / nsplit;
@@ -464,7 +502,6 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
       else
         j_pass_kernel<1><<<g, 256, 0, st>>>((const double2*)c->Bt, rho + (long)s0 * naux, (double2*)part, E2, naux, rows_per_split);
       LAUNCH_CHECK(c);
-      dim3 gf((n + 127) / 128, n);
       j_finalize_kernel<<<gf, 128, 0, st>>>(part, c->d_inv.p, d_J + (long)s0 * nn, n, c->nb, E, nsplit, ns);
       LAUNCH_CHECK(c);
     }
@@ -675,6 +712,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "overlap") c->overlap = (int)value;
   else if (k == "dist_eig") c->dist_eig = (int)value;
   else if (k == "panel_stages") c->panel_stages = (int)value;
+  else if (k == "jpass_variant") c->jpass_variant = (int)value;
   else if (k == "eig_mode") { c->eig_mode = (int)value; c->sub_valid = false; }
   else return NBD_ERR_ARG;
   return NBD_OK;

@@ -15,9 +15,9 @@
 
 namespace nbd {
 
-constexpr int SUB_ROWS = 32;    // output rows per CTA
-constexpr int SUB_JCHUNK = 32;  // contraction chunk
-constexpr int SUB_MAX_SPLIT = 8;
+constexpr int SUB_ROWS = 64;    // output rows per CTA (4 warps x 16 rows)
+constexpr int SUB_JCHUNK = 32;  // contraction chunk per pipeline stage
+constexpr int SUB_MAX_SPLIT = 16;
 
 struct SubApplyArgs {
   const double* A;  // [batch][n][n] symmetric
@@ -30,37 +30,49 @@ struct SubApplyArgs {
   double alpha[2], shift[2], beta[2];  // per batch entry: out = alpha * (A Y - shift Y) - beta Z
 };
 
-// out = alpha (A Y - shift Y) - beta Z, the contraction split over `nsplit` CTAs per row block; the last CTA to
-// finish a row block sums the partials in index order (deterministic) and applies the epilogue.
 template <int KB>
-__global__ void __launch_bounds__(256) sub_apply_kernel(SubApplyArgs a) {
-  __shared__ double As[2][SUB_ROWS][SUB_JCHUNK + 1];
-  __shared__ double Ys[2][SUB_JCHUNK][KB];
+constexpr int sub_apply_smem_bytes() {
+  return (2 * SUB_ROWS * (SUB_JCHUNK + 4) + 2 * SUB_JCHUNK * (KB + 4)) * 8;
+}
+
+// out = alpha (A Y - shift Y) - beta Z.  FP64 tensor-core (DMMA m8n8k4) skinny product: a CTA owns 64 rows and a
+// slice of the contraction index (split-K over `nsplit` CTAs per row block, two-stage cp.async ring); the last
+// CTA to finish a row block sums the partials in index order (deterministic) and applies the epilogue.
+template <int KB>
+__global__ void __launch_bounds__(128) sub_apply_kernel(SubApplyArgs a) {
+  constexpr int A_LD = SUB_JCHUNK + 4, Y_LD = KB + 4, NI = KB / 8;
+  extern __shared__ __align__(16) double sub_smem[];
+  double(*As)[SUB_ROWS * A_LD] = reinterpret_cast<double(*)[SUB_ROWS * A_LD]>(sub_smem);
+  double(*Ys)[SUB_JCHUNK * Y_LD] = reinterpret_cast<double(*)[SUB_JCHUNK * Y_LD]>(sub_smem + 2 * SUB_ROWS * A_LD);
   __shared__ unsigned int is_last;
   const int rb = blockIdx.x, sp = blockIdx.y, b = blockIdx.z;
-  const int n = a.n, tid = threadIdx.x;
+  const int n = a.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;
   const double* A = a.A + (long)b * n * n;
   const double* Y = a.Y + (long)b * n * KB;
   const int nchunk = (n + SUB_JCHUNK - 1) / SUB_JCHUNK;
   const int c0 = (int)((long)nchunk * sp / a.nsplit), c1 = (int)((long)nchunk * (sp + 1) / a.nsplit);
-  constexpr int TPR = 256 / KB;            // threads along rows
-  constexpr int RPT = SUB_ROWS / TPR;      // rows per thread
-  const int col = tid % KB, rgrp = tid / KB;
-  double acc[RPT];
+  double acc[2][NI][2];
 #pragma unroll
-  for (int q = 0; q < RPT; ++q) acc[q] = 0.0;
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   auto load = [&](int ch, int buf) {
     const int j0 = ch * SUB_JCHUNK;
-    for (int e = tid; e < SUB_ROWS * SUB_JCHUNK; e += 256) {
+#pragma unroll
+    for (int q = 0; q < SUB_ROWS * SUB_JCHUNK / 128; ++q) {
+      const int e = tid + 128 * q;
       const int r = e / SUB_JCHUNK, j = e % SUB_JCHUNK;
       const int gi = rb * SUB_ROWS + r, gj = j0 + j;
       const bool ok = gi < n && gj < n;
-      cp_async8(&As[buf][r][j], ok ? A + (long)gi * n + gj : A, ok);
+      cp_async8(&As[buf][r * A_LD + j], ok ? A + (long)gi * n + gj : A, ok);
     }
-    for (int e = tid; e < SUB_JCHUNK * KB; e += 256) {
+#pragma unroll
+    for (int q = 0; q < SUB_JCHUNK * KB / 128; ++q) {
+      const int e = tid + 128 * q;
       const int j = e / KB, c = e % KB;
       const bool ok = j0 + j < n;
-      cp_async8(&Ys[buf][j][c], ok ? Y + (long)(j0 + j) * KB + c : Y, ok);
+      cp_async8(&Ys[buf][j * Y_LD + c], ok ? Y + (long)(j0 + j) * KB + c : Y, ok);
     }
   };
   if (c0 < c1) load(c0, 0);
@@ -71,20 +83,32 @@ __global__ void __launch_bounds__(256) sub_apply_kernel(SubApplyArgs a) {
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-#pragma unroll 8
-    for (int j = 0; j < SUB_JCHUNK; ++j) {
-      const double y = Ys[buf][j][col];
+    const double* as = &As[buf][(16 * warp + gq) * A_LD + tq];
+    const double* ys = &Ys[buf][tq * Y_LD + gq];
 #pragma unroll
-      for (int q = 0; q < RPT; ++q) acc[q] = fma(As[buf][rgrp + TPR * q][j], y, acc[q]);
+    for (int k4 = 0; k4 < SUB_JCHUNK; k4 += 4) {
+      double af[2], bf[NI];
+      af[0] = as[k4];
+      af[1] = as[8 * A_LD + k4];
+#pragma unroll
+      for (int j = 0; j < NI; ++j) bf[j] = ys[k4 * Y_LD + 8 * j];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) dmma(acc[i][j], af[i], bf[j]);
     }
     __syncthreads();
   }
   cp_async_wait<0>();
   double* part = a.part + (((long)b * a.nsplit + sp) * n) * KB;
 #pragma unroll
-  for (int q = 0; q < RPT; ++q) {
-    const int gi = rb * SUB_ROWS + rgrp + TPR * q;
-    if (gi < n) part[(long)gi * KB + col] = acc[q];
+  for (int i = 0; i < 2; ++i) {
+    const int gi = rb * SUB_ROWS + 16 * warp + 8 * i + gq;
+    if (gi < n) {
+#pragma unroll
+      for (int j = 0; j < NI; ++j)
+        *reinterpret_cast<double2*>(&part[(long)gi * KB + 8 * j + 2 * tq]) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
   }
   __threadfence();
   __syncthreads();
@@ -99,15 +123,38 @@ __global__ void __launch_bounds__(256) sub_apply_kernel(SubApplyArgs a) {
   const double alpha = a.alpha[b], shift = a.shift[b], beta = a.beta[b];
   const double* Z = a.Z ? a.Z + (long)b * n * KB : nullptr;
   double* out = a.out + (long)b * n * KB;
+  // epilogue of the row block: SUB_ROWS * KB outputs, all partial loads of a thread issued independently
+  constexpr int OPT = SUB_ROWS * KB / 128;  // outputs per thread
+  double s[OPT];
+  long off[OPT];
+  bool ok[OPT];
 #pragma unroll
-  for (int q = 0; q < RPT; ++q) {
-    const int gi = rb * SUB_ROWS + rgrp + TPR * q;
-    if (gi >= n) continue;
-    double s = 0.0;
-    for (int k = 0; k < a.nsplit; ++k) s += a.part[(((long)b * a.nsplit + k) * n + gi) * KB + col];
-    double v = alpha * (s - shift * Y[(long)gi * KB + col]);
-    if (Z) v -= beta * Z[(long)gi * KB + col];
-    out[(long)gi * KB + col] = v;
+  for (int q = 0; q < OPT; ++q) {
+    const int e = tid + 128 * q;
+    const int gi = rb * SUB_ROWS + e / KB;
+    ok[q] = gi < n;
+    off[q] = (long)min(gi, n - 1) * KB + e % KB;
+    s[q] = 0.0;
+  }
+  const long pstride = (long)n * KB;
+  const double* pbase = a.part + (long)b * a.nsplit * pstride;
+  for (int k = 0; k < a.nsplit; k += 2) {
+    double v0[OPT], v1[OPT];
+    const bool two = k + 1 < a.nsplit;
+#pragma unroll
+    for (int q = 0; q < OPT; ++q) {
+      v0[q] = __ldcg(pbase + k * pstride + off[q]);
+      v1[q] = two ? __ldcg(pbase + (k + 1) * pstride + off[q]) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < OPT; ++q) s[q] = (s[q] + v0[q]) + v1[q];
+  }
+#pragma unroll
+  for (int q = 0; q < OPT; ++q) {
+    if (!ok[q]) continue;
+    double v = alpha * (s[q] - shift * Y[off[q]]);
+    if (Z) v -= beta * Z[off[q]];
+    out[off[q]] = v;
   }
 }
 

@@ -55,12 +55,18 @@ static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double
   a.n = n;
   const int nrb = (n + SUB_ROWS - 1) / SUB_ROWS;
   // latency-bound kernel over L2-resident data: many short CTAs (about 4-5 per SM) beat few long ones
-  a.nsplit = std::max(1, std::min(SUB_MAX_SPLIT, (5 * c->sm_count) / std::max(1, nrb * c->nspin)));
+  a.nsplit = std::max(1, std::min(SUB_MAX_SPLIT, (3 * c->sm_count) / std::max(1, nrb * c->nspin)));
   for (int b = 0; b < 2; ++b) {
     a.alpha[b] = alpha[b]; a.shift[b] = shift[b]; a.beta[b] = beta[b];
   }
   dim3 g(nrb, a.nsplit, c->nspin);
-  sub_apply_kernel<KB><<<g, 256, 0, c->stream>>>(a);
+  constexpr int smem = sub_apply_smem_bytes<KB>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    NBD_CUDA(cudaFuncSetAttribute(sub_apply_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  sub_apply_kernel<KB><<<g, 128, smem, c->stream>>>(a);
   LAUNCH_CHECK(c);
   ++c->sub_applies;
 }
