@@ -480,6 +480,9 @@ extern "C" int nbd_mu_scf(nbd_ctx* c, int max_cycle, double conv_tol, double e_n
     c->timers.reset();
     NBD_REQUIRE(c->scf_ready && c->projector == NBD_MU_SHIFT, NBD_ERR_STATE, "nbd_scf_setup(projector = NBD_MU_SHIFT) first");
     NBD_REQUIRE(dm0 && max_cycle >= 1, NBD_ERR_ARG, "dm0 is required (PySCF's minao guess needs basis data)");
+    // the reference's mu path is spin-resolved only: _env_projector indexes dm_enviro[0] (nbed/driver.py:439) and
+    // the driver always builds UHF/UKS objects, so a rank-2 call has no reference behaviour to reproduce
+    NBD_REQUIRE(c->nspin == 2, NBD_ERR_UNSUPPORTED, "mu-shift embedding is spin-resolved (rank-3 inputs) in the reference");
     const int n = c->nao, ns = c->nspin;
     const long nn = (long)n * n;
     const double conv_tol_grad = std::sqrt(conv_tol);

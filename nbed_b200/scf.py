@@ -249,6 +249,9 @@ def mu_embed(localized_scf, embedding_potential, dm_enviro, mu_level_shift: floa
         raise ValueError("dm0 is required: PySCF's 'minao' guess needs atomic basis data that is outside the hot path")
     s = localized_scf.get_ovlp()
     g = np.asarray(dm_enviro, dtype=np.float64)
+    if g.ndim != 3 or not localized_scf.unrestricted:
+        # NbedDriver._env_projector indexes dm_enviro[0] unconditionally (nbed/driver.py:439): rank-3 only
+        raise ValueError("mu-shift embedding is spin-resolved in the reference: pass (2, n, n) arrays and a B200UHF")
     v = np.asarray(embedding_potential, dtype=np.float64)
     ctx = localized_scf.ctx
     hcore_std = localized_scf.get_hcore()
