@@ -31,6 +31,7 @@ from nbed_b200 import synthetic as syn  # noqa: E402
 WORKLOADS = {
     # name: (config key, description)
     "C4": ("C4_h2o32_def2tzvp", "synthetic (H2O)32/def2-TZVP-shaped Huzinaga embedded SCF (n=1376, naux=4128, o=5/spin, UHF)"),
+    "C4o20": ("C4_h2o32_def2tzvp_o20", "synthetic (H2O)32/def2-TZVP-shaped, 20 active occupied per spin (n=1376, naux=4128, UHF): tensor-bound regime"),
     "C5": ("C5_h2o16_def2tzvp", "synthetic (H2O)16/def2-TZVP-shaped (n=688, naux=2064, o=5/spin, UHF)"),
     "C3": ("C3_ethanol_ccpvtz", "synthetic ethanol/cc-pVTZ-shaped (n=174, naux=522, o=9/spin, UHF)"),
 }

@@ -207,18 +207,26 @@ template <int NB>
 __device__ __forceinline__ void xk_task_row(double (&acc)[4][NB][2], const double* __restrict__ tile,
                                             const double* const (&crow)[NB], int colbase, int gq, int tq,
                                             const int (&xoff)[4]) {
+  // fragments of step ks+1 are loaded before the DMMAs of step ks issue (register double buffering)
+  double a[2][4], b[2][NB];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) a[0][mi] = tile[(8 * mi + gq) * 32 + xoff[0]];
+#pragma unroll
+  for (int ni = 0; ni < NB; ++ni) b[0][ni] = crow[ni][colbase + tq];
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    double a[4], b[NB];
-    const int co = ((ks >> 2) << 4) + xoff[ks & 3];
+    const int cur = ks & 1, nxt = cur ^ 1;
+    if (ks + 1 < 8) {
+      const int co = (((ks + 1) >> 2) << 4) + xoff[(ks + 1) & 3];
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) a[mi] = tile[(8 * mi + gq) * 32 + co];
+      for (int mi = 0; mi < 4; ++mi) a[nxt][mi] = tile[(8 * mi + gq) * 32 + co];
 #pragma unroll
-    for (int ni = 0; ni < NB; ++ni) b[ni] = crow[ni][colbase + 4 * ks + tq];
+      for (int ni = 0; ni < NB; ++ni) b[nxt][ni] = crow[ni][colbase + 4 * (ks + 1) + tq];
+    }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < NB; ++ni) dmma(acc[mi][ni], a[mi], b[ni]);
+      for (int ni = 0; ni < NB; ++ni) dmma(acc[mi][ni], a[cur][mi], b[cur][ni]);
   }
 }
 
@@ -226,17 +234,24 @@ template <int NB>
 __device__ __forceinline__ void xk_task_col(double (&acc)[4][NB][2], const double* __restrict__ tile,
                                             const double* const (&crow)[NB], int colbase, int tq,
                                             const int (&yoff)[4]) {
+  double a[2][4], b[2][NB];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) a[0][mi] = tile[tq * 32 + yoff[mi]];
+#pragma unroll
+  for (int ni = 0; ni < NB; ++ni) b[0][ni] = crow[ni][colbase + tq];
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    double a[4], b[NB];
+    const int cur = ks & 1, nxt = cur ^ 1;
+    if (ks + 1 < 8) {
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) a[mi] = tile[(4 * ks + tq) * 32 + yoff[mi]];
+      for (int mi = 0; mi < 4; ++mi) a[nxt][mi] = tile[(4 * (ks + 1) + tq) * 32 + yoff[mi]];
 #pragma unroll
-    for (int ni = 0; ni < NB; ++ni) b[ni] = crow[ni][colbase + 4 * ks + tq];
+      for (int ni = 0; ni < NB; ++ni) b[nxt][ni] = crow[ni][colbase + 4 * (ks + 1) + tq];
+    }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < NB; ++ni) dmma(acc[mi][ni], a[mi], b[ni]);
+      for (int ni = 0; ni < NB; ++ni) dmma(acc[mi][ni], a[cur][mi], b[cur][ni]);
   }
 }
 

@@ -19,6 +19,8 @@ CONFIGS = {
     "C2_h2o_ccpvdz": dict(n=24, naux=72, nocc=4, n_env=1, m=12),
     "C3_ethanol_ccpvtz": dict(n=174, naux=522, nocc=9, n_env=4, m=24),
     "C4_h2o32_def2tzvp": dict(n=1376, naux=4128, nocc=5, n_env=155, m=40),
+    # the same system with a 20-orbital active region per spin (the FP64-tensor-bound regime)
+    "C4_h2o32_def2tzvp_o20": dict(n=1376, naux=4128, nocc=20, n_env=140, m=40),
     "C5_h2o16_def2tzvp": dict(n=688, naux=2064, nocc=5, n_env=75, m=40),
 }
 
