@@ -127,6 +127,15 @@ def cpu_iterations_per_s(key: str, steps: int, naux_sample: int):
     from oracle import nbed_restatement as nr
     from oracle import pyscf_restatement as ps
 
+    # all host threads, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     cfg, p = build_problem(key)
     naux = cfg["naux"]
     naux_sample = min(naux_sample, naux)
