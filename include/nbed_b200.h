@@ -136,6 +136,12 @@ int nbd_ao2mo(nbd_ctx* ctx, int m, const double* ca, const double* cb, double* o
  * hcore [nspin_h][nao][nao] (nspin_h = 1 or 2), out [2][m][m]. */
 int nbd_one_body(nbd_ctx* ctx, int m, int nspin_h, const double* hcore, const double* ca, const double* cb,
                  double* out);
+/* Replaces: HamiltonianBuilder.build() end to end (nbed/ham_builder.py:218-254) = _one_body_integrals +
+ * _two_body_integrals + _spinorb_from_spatial + the 0.5 factor, with the MO integrals kept on the device
+ * (only h1 [2m][2m] and h2 [2m]^4 are copied back).  Arguments as nbd_one_body / nbd_ao2mo /
+ * nbd_spinorb_from_spatial. */
+int nbd_build_hamiltonian(nbd_ctx* ctx, int m, int nspin_h, const double* hcore, const double* ca, const double* cb,
+                          double eq_tol, double two_body_scale, double* h1, double* h2);
 /* Replaces: HamiltonianBuilder._spinorb_from_spatial + the 0.5 factor of build()
  * (nbed/ham_builder.py:158-216,254).  one [2][m][m], two [4][m][m][m][m] (host);
  * h1 [2m][2m], h2 [2m][2m][2m][2m] (host); |x| < eq_tol -> 0; h2 is scaled by two_body_scale (0.5). */

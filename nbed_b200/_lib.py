@@ -19,7 +19,7 @@ EXPORTS = [
     "nbd_launch_count", "nbd_host_alloc", "nbd_host_free", "nbd_comm_unique_id", "nbd_comm_init", "nbd_cderi_alloc", "nbd_cderi_upload",
     "nbd_cderi_synth", "nbd_cderi_download", "nbd_jk", "nbd_jk_dm", "nbd_scf_setup", "nbd_huzinaga_scf",
     "nbd_mu_scf", "nbd_scf_bench_init", "nbd_scf_bench_iteration", "nbd_ao2mo", "nbd_one_body",
-    "nbd_spinorb_from_spatial",
+    "nbd_spinorb_from_spatial", "nbd_build_hamiltonian",
 ]
 
 
@@ -81,6 +81,7 @@ def load() -> C.CDLL:
         "nbd_ao2mo": (I, [P, I, P, P, P]),
         "nbd_one_body": (I, [P, I, I, P, P, P, P]),
         "nbd_spinorb_from_spatial": (I, [P, I, P, P, D, D, P, P]),
+        "nbd_build_hamiltonian": (I, [P, I, I, P, P, P, D, D, P, P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -117,8 +117,8 @@ class B200Context:
         sg = None
         if signs is not None:
             sg = np.concatenate([f64(s).ravel() for s in signs]) if ncol.sum() else np.zeros(1)
-        vj = pinned_empty((nset, n, n)) if with_j else None
-        vk = pinned_empty((nset, n, n)) if with_k else None
+        vj = np.empty((nset, n, n)) if with_j else None
+        vk = np.empty((nset, n, n)) if with_k else None
         self._ck(self._lib.nbd_jk(self._h, nset, ptr(ncol), ptr(flat), ptr(sg), ptr(vj), ptr(vk)))
         return vj, vk
 
@@ -144,7 +144,7 @@ class B200Context:
     def huzinaga_scf(self, max_cycle, conv_tol, dm_conv_tol=1e-6, use_diis=True, dm0=None):
         n, ns = self.nao, self._nspin
         shape = (n, n) if ns == 1 else (2, n, n)
-        c, dm, huz = pinned_empty(shape), pinned_empty(shape), pinned_empty(shape)
+        c, dm, huz = np.empty(shape), np.empty(shape), np.empty(shape)
         e = np.empty(shape[:-1])
         trace = np.zeros((max_cycle, 3))
         res = ScfResult()
@@ -159,7 +159,7 @@ class B200Context:
     def mu_scf(self, max_cycle, conv_tol, e_nuc, dm0):
         n, ns = self.nao, self._nspin
         shape = (n, n) if ns == 1 else (2, n, n)
-        c, dm, vhf = pinned_empty(shape), pinned_empty(shape), pinned_empty(shape)
+        c, dm, vhf = np.empty(shape), np.empty(shape), np.empty(shape)
         e, occ = np.empty(shape[:-1]), np.empty(shape[:-1])
         trace = np.zeros((max_cycle + 1, 3))
         res = ScfResult()
@@ -185,7 +185,7 @@ class B200Context:
         ca = f64(ca)
         m = ca.shape[1]
         cbp = None if cb is None else f64(cb)
-        out = pinned_empty((4, m, m, m, m))
+        out = np.empty((4, m, m, m, m))
         self._ck(self._lib.nbd_ao2mo(self._h, m, ptr(ca), ptr(cbp), ptr(out)))
         return out
 
@@ -202,10 +202,24 @@ class B200Context:
         one, two = f64(one), f64(two)
         m = one.shape[-1]
         h1 = np.empty((2 * m, 2 * m))
-        h2 = pinned_empty((2 * m,) * 4)
+        h2 = np.empty((2 * m,) * 4)
         self._ck(self._lib.nbd_spinorb_from_spatial(self._h, m, ptr(one), ptr(two), float(eq_tol),
                                                     float(two_body_scale), ptr(h1), ptr(h2)))
         return h1, h2
 
+
+    def build_hamiltonian(self, hcore, ca, cb=None, eq_tol=1e-8, two_body_scale=0.5):
+        """(h1 [2m, 2m], h2 [2m]^4) of HamiltonianBuilder.build() with the MO integrals kept on the device."""
+        hcore, ca = f64(hcore), f64(ca)
+        m = ca.shape[1]
+        nspin_h = 1 if hcore.ndim == 2 else 2
+        cbp = None if cb is None else f64(cb)
+        h1 = np.empty((2 * m, 2 * m))
+        h2 = np.empty((2 * m,) * 4)
+        self._ck(self._lib.nbd_build_hamiltonian(self._h, m, nspin_h, ptr(hcore), ptr(ca), ptr(cbp), float(eq_tol),
+                                                 float(two_body_scale), ptr(h1), ptr(h2)))
+        return h1, h2
+
+    
 
 __all__ = ["B200Context", "NBD_HUZINAGA", "NBD_MU_SHIFT", "NbdError"]

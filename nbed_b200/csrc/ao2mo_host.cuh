@@ -18,11 +18,8 @@ static void ao2mo_stage_mos(nbd_ctx* c, const double* C, int m, int row0) {
   NBD_CUDA(cudaStreamSynchronize(c->stream));
 }
 
-extern "C" int nbd_ao2mo(nbd_ctx* c, int m, const double* ca, const double* cb, double* out) {
-  return guarded(c, [&] {
-    c->timers.reset();
-    NBD_REQUIRE(c->Bt, NBD_ERR_STATE, "nbd_cderi_alloc first");
-    NBD_REQUIRE(m >= 1 && ca && out, NBD_ERR_ARG, "bad m / pointers");
+// Device part of the transform: leaves out[blk][p][r][s][q] = (pq|rs) (4 blocks) in c->eri_phys.
+static void ao2mo_device(nbd_ctx* c, int m, const double* ca, const double* cb) {
     const int n_ld = c->n_ld, naux = c->naux;
     const bool restricted = (cb == nullptr || cb == ca);
     const int nsp = restricted ? 1 : 2;
@@ -76,11 +73,39 @@ extern "C" int nbd_ao2mo(nbd_ctx* c, int m, const double* ca, const double* cb, 
           chem_to_phys_kernel<<<g, 256, 0, c->stream>>>(src, phys + (long)blk * m4, m, (!restricted && blk == 3) ? 1 : 0);
           LAUNCH_CHECK(c);
         }
-        d2h(c, out, phys, (size_t)4 * m4);
       }
     }
+}
+
+extern "C" int nbd_ao2mo(nbd_ctx* c, int m, const double* ca, const double* cb, double* out) {
+  return guarded(c, [&] {
+    c->timers.reset();
+    NBD_REQUIRE(c->Bt, NBD_ERR_STATE, "nbd_cderi_alloc first");
+    NBD_REQUIRE(m >= 1 && ca && out, NBD_ERR_ARG, "bad m / pointers");
+    ao2mo_device(c, m, ca, cb);
+    d2h(c, out, c->eri_phys.p, (size_t)4 * m * m * m * m);
     finish_call(c);
   });
+}
+
+// out (device, c->red_out) [2][m][m] = C_s^T h_s C_s
+static double* one_body_device(nbd_ctx* c, int m, int nspin_h, const double* hcore, const double* ca, const double* cb) {
+  const int n = c->nao;
+  const long nn = (long)n * n, nm = (long)n * m, m2 = (long)m * m;
+  if (!cb) cb = ca;
+  double* h = c->T1.ensure((size_t)2 * nn);
+  double* C = c->mo_c.ensure((size_t)2 * nm);
+  double* T = c->T2.ensure((size_t)std::max(2 * nn, 2 * nm));
+  double* o = c->red_out.ensure((size_t)std::max<long>(64, 2 * m2));
+  h2d(c, h, hcore, (size_t)nspin_h * nn);
+  h2d(c, C, ca, nm);
+  h2d(c, C + nm, cb, nm);
+  for (int s = 0; s < 2; ++s) {
+    const double* hs = h + (nspin_h == 2 ? s * nn : 0);
+    gemm_nn(c, n, m, n, hs, n, C + s * nm, m, T + s * nm, m);
+    gemm_tn(c, m, m, n, C + s * nm, m, T + s * nm, m, o + s * m2, m);
+  }
+  return o;
 }
 
 extern "C" int nbd_one_body(nbd_ctx* c, int m, int nspin_h, const double* hcore, const double* ca, const double* cb,
@@ -89,22 +114,38 @@ extern "C" int nbd_one_body(nbd_ctx* c, int m, int nspin_h, const double* hcore,
     c->timers.reset();
     NBD_REQUIRE(c->nao > 0, NBD_ERR_STATE, "nbd_cderi_alloc first (nao)");
     NBD_REQUIRE(m >= 1 && (nspin_h == 1 || nspin_h == 2) && hcore && ca && out, NBD_ERR_ARG, "bad arguments");
-    const int n = c->nao;
-    const long nn = (long)n * n, nm = (long)n * m, m2 = (long)m * m;
-    if (!cb) cb = ca;
-    double* h = c->T1.ensure((size_t)2 * nn);
-    double* C = c->mo_c.ensure((size_t)2 * nm);
-    double* T = c->T2.ensure((size_t)std::max(2 * nn, 2 * nm));
-    double* o = c->red_out.ensure((size_t)std::max<long>(64, 2 * m2));
-    h2d(c, h, hcore, (size_t)nspin_h * nn);
-    h2d(c, C, ca, nm);
-    h2d(c, C + nm, cb, nm);
-    for (int s = 0; s < 2; ++s) {
-      const double* hs = h + (nspin_h == 2 ? s * nn : 0);
-      gemm_nn(c, n, m, n, hs, n, C + s * nm, m, T + s * nm, m);
-      gemm_tn(c, m, m, n, C + s * nm, m, T + s * nm, m, o + s * m2, m);
+    const double* o = one_body_device(c, m, nspin_h, hcore, ca, cb);
+    d2h(c, out, o, (size_t)2 * m * m);
+    finish_call(c);
+  });
+}
+
+// Replaces HamiltonianBuilder.build() end to end (nbed/ham_builder.py:218-254): one-body transform, the four
+// two-body blocks, the spin-orbital scatter with the EQ_TOLERANCE truncation and the 0.5 factor - all on the
+// device; only h1 [2m][2m] and h2 [2m]^4 cross PCIe.
+extern "C" int nbd_build_hamiltonian(nbd_ctx* c, int m, int nspin_h, const double* hcore, const double* ca,
+                                     const double* cb, double eq_tol, double two_body_scale, double* h1, double* h2) {
+  return guarded(c, [&] {
+    c->timers.reset();
+    NBD_REQUIRE(c->Bt, NBD_ERR_STATE, "nbd_cderi_alloc first");
+    NBD_REQUIRE(m >= 1 && (nspin_h == 1 || nspin_h == 2) && hcore && ca && h1 && h2, NBD_ERR_ARG, "bad arguments");
+    const long m2 = (long)m * m, m4 = m2 * m2, q2 = 4 * m2, q4 = 16 * m4;
+    {
+      StageScope ts_all(c->timers, c->stream, "build_total");
+      const double* one = one_body_device(c, m, nspin_h, hcore, ca, cb);
+      double* d_h1 = c->red_part.ensure((size_t)std::max<long>(q2, (long)REDUCE_BLOCKS * 9));
+      spinorb_one_kernel<<<grid1(q2, 256), 256, 0, c->stream>>>(one, d_h1, m, eq_tol);
+      LAUNCH_CHECK(c);
+      ao2mo_device(c, m, ca, cb);  // -> c->eri_phys (uses T1/T2-free workspaces only)
+      double* d_h2 = c->Lbuf.ensure((size_t)q4);  // L is dead after the (pq|rs) GEMMs
+      {
+        StageScope ts(c->timers, c->stream, "spinorb");
+        spinorb_two_kernel<<<grid1(q4, 256), 256, 0, c->stream>>>(c->eri_phys.p, d_h2, m, eq_tol, two_body_scale);
+        LAUNCH_CHECK(c);
+      }
+      d2h(c, h1, d_h1, (size_t)q2);
+      d2h(c, h2, d_h2, (size_t)q4);
     }
-    d2h(c, out, o, (size_t)2 * m2);
     finish_call(c);
   });
 }

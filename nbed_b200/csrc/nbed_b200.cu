@@ -10,6 +10,7 @@
 #include <array>
 #include <cmath>
 #include <cstring>
+#include <future>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -192,6 +193,7 @@ struct nbd_ctx {
   cudaStream_t stream2 = nullptr;
   cusolverDnHandle_t solver2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
   int overlap = 1;
   int dist_eig = 1;
   int jpass_variant = 0;  // 0: TMA-fed persistent pass 2, 1: LDG streaming pass 2
@@ -641,11 +643,86 @@ static void finish_call(nbd_ctx* c) {
   NBD_CUDA(cudaStreamSynchronize(c->stream));
   c->timers.resolve();
 }
+// Large copies to / from PAGEABLE host memory (numpy arrays of the caller) are pipelined through two page-locked
+// staging buffers: the DMA of chunk i overlaps the (multi-threaded) host memcpy of chunk i-1.  cudaMemcpyAsync on
+// pageable memory reaches ~5 GB/s on these hosts; page-locking the caller's buffer per call costs more than that.
+constexpr size_t STAGE_CHUNK = 16u << 20;
+static bool host_is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+static void parallel_memcpy(char* dst, const char* src, size_t n) {
+  constexpr int T = 4;
+  if (n < (4u << 20)) {
+    memcpy(dst, src, n);
+    return;
+  }
+  std::future<void> f[T - 1];
+  const size_t part = (n / T + 63) & ~(size_t)63;
+  for (int t = 1; t < T; ++t) {
+    const size_t o = std::min(n, part * t), e = std::min(n, part * (t + 1));
+    f[t - 1] = std::async(std::launch::async, [=] { memcpy(dst + o, src + o, e - o); });
+  }
+  memcpy(dst, src, std::min(n, part));
+  for (auto& x : f) x.get();
+}
+static void staged_copy(nbd_ctx* c, char* host, char* dev, size_t bytes, bool to_host) {
+  char* st = (char*)c->pinned.ensure(2 * STAGE_CHUNK);
+  if (!c->ev_stage[0]) {
+    NBD_CUDA(cudaEventCreateWithFlags(&c->ev_stage[0], cudaEventDisableTiming));
+    NBD_CUDA(cudaEventCreateWithFlags(&c->ev_stage[1], cudaEventDisableTiming));
+  }
+  const size_t nch = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+  if (to_host) {
+    std::future<void> fut[2];
+    for (size_t i = 0; i < nch; ++i) {
+      const int b = (int)(i & 1);
+      const size_t off = i * STAGE_CHUNK, n = std::min(STAGE_CHUNK, bytes - off);
+      if (fut[b].valid()) fut[b].get();  // staging buffer b is free again
+      NBD_CUDA(cudaMemcpyAsync(st + b * STAGE_CHUNK, dev + off, n, cudaMemcpyDeviceToHost, c->stream));
+      NBD_CUDA(cudaEventRecord(c->ev_stage[b], c->stream));
+      cudaEvent_t ev = c->ev_stage[b];
+      char* src = st + b * STAGE_CHUNK;
+      char* dst = host + off;
+      fut[b] = std::async(std::launch::async, [=] {
+        cudaEventSynchronize(ev);
+        parallel_memcpy(dst, src, n);
+      });
+    }
+    for (auto& f : fut)
+      if (f.valid()) f.get();
+  } else {
+    for (size_t i = 0; i < nch; ++i) {
+      const int b = (int)(i & 1);
+      const size_t off = i * STAGE_CHUNK, n = std::min(STAGE_CHUNK, bytes - off);
+      if (i >= 2) NBD_CUDA(cudaEventSynchronize(c->ev_stage[b]));  // DMA out of staging buffer b has finished
+      parallel_memcpy(st + b * STAGE_CHUNK, host + off, n);
+      NBD_CUDA(cudaMemcpyAsync(dev + off, st + b * STAGE_CHUNK, n, cudaMemcpyHostToDevice, c->stream));
+      NBD_CUDA(cudaEventRecord(c->ev_stage[b], c->stream));
+    }
+    NBD_CUDA(cudaEventSynchronize(c->ev_stage[0]));
+    NBD_CUDA(cudaEventSynchronize(c->ev_stage[1]));
+  }
+}
 static void h2d(nbd_ctx* c, double* dst, const double* src, size_t count) {
-  NBD_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  const size_t bytes = count * sizeof(double);
+  if (bytes >= (8u << 20) && host_is_pageable(src)) {
+    staged_copy(c, (char*)src, (char*)dst, bytes, false);
+    return;
+  }
+  NBD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
 }
 static void d2h(nbd_ctx* c, double* dst, const double* src, size_t count) {
-  NBD_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  const size_t bytes = count * sizeof(double);
+  if (bytes >= (8u << 20) && host_is_pageable(dst)) {
+    staged_copy(c, (char*)dst, (char*)src, bytes, true);
+    return;
+  }
+  NBD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
 }
 
 extern "C" {
@@ -694,6 +771,8 @@ int nbd_destroy(nbd_ctx* c) {
   if (c->solver2) cusolverDnDestroy(c->solver2);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  for (auto e : c->ev_stage)
+    if (e) cudaEventDestroy(e);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;

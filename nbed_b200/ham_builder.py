@@ -56,10 +56,16 @@ class HamiltonianBuilder:
     def build(self):  # :218-254
         if self.n_frozen_virt != 0:
             self.scf_method = reduce_virtuals(self.scf_method, self.n_frozen_virt)
-        one = self._one_body_integrals
-        two = self._two_body_integrals
-        # the 0.5 of the return statement (:254) is fused into the scatter kernel
-        h1, h2 = self._spinorb_from_spatial(one, two, two_body_scale=0.5)
+        # one fused device call: one-body + four two-body blocks + spin-orbital scatter (EQ_TOLERANCE, the 0.5 of :254)
+        c = np.asarray(self.scf_method.mo_coeff)
+        hcore = np.asarray(self.scf_method.get_hcore())
+        ctx = self.scf_method.ctx
+        if not self._restricted:
+            if c[0].shape[1] != c[1].shape[1]:
+                raise HamiltonianBuilderError("Must localize the same number of alpha and beta orbitals.")  # :109-112
+            h1, h2 = ctx.build_hamiltonian(hcore, c[0], c[1], EQ_TOLERANCE, 0.5)
+        else:
+            h1, h2 = ctx.build_hamiltonian(hcore, c, None, EQ_TOLERANCE, 0.5)
         return self.constant_e_shift, h1, h2
 
 
