@@ -688,7 +688,9 @@ static void staged_copy(nbd_ctx* c, char* host, char* dev, size_t bytes, bool to
       cudaEvent_t ev = c->ev_stage[b];
       char* src = st + b * STAGE_CHUNK;
       char* dst = host + off;
+      const int dev_id = c->device;
       fut[b] = std::async(std::launch::async, [=] {
+        cudaSetDevice(dev_id);
         cudaEventSynchronize(ev);
         parallel_memcpy(dst, src, n);
       });
