@@ -309,8 +309,12 @@ def run_b200(args):
         roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": frac_hbm}
     else:
         roof = {"bound": "tensor", "achieved": ach_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": frac_tensor}
-    roof.update({"kernel": {"jk_x": "symm_panel_kernel", "jk_j": "j_pass_kernel", "jk_k": "gemm_dmma_kernel (K Gram)"}[dom],
-                 "traffic": None, "ms_per_launch": stages[dom], "peak_source": peak_src,
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of this
+    # very configuration (profiles/ncu_r01_raw_key_metrics.csv, capture r01c); other shapes / shard sizes were not captured
+    traffic = 32.000677e9 + 0.444601e9 if (dom == "jk_x" and args.workload == "C4" and world == 1) else None
+    roof.update({"kernel": {"jk_x": "symm_panel_kernel", "jk_j": "j_pass_tma_kernel", "jk_k": "gemm_dmma_kernel (K Gram)"}[dom],
+                 "traffic": traffic, "algorithmic_bytes": kern[dom]["bytes"], "algorithmic_flops": kern[dom]["flops"],
+                 "ms_per_launch": stages[dom], "peak_source": peak_src,
                  "other_axis": {"hbm_frac": frac_hbm, "fp64_tensor_frac": frac_tensor,
                                 "fp64_peak_tflops": FP64_PEAK_TFLOPS}})
     # whole J/K against the two-pass model of SURVEY.md 8(d): max(F/P64, B/BW) / t
