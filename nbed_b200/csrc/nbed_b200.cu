@@ -232,13 +232,14 @@ struct nbd_ctx {
   int nspin = 0, projector = 0;
   int nelec[2] = {0, 0};
   double mu = 0.0;
-  DBuf<double> S, Xh, hcore, heff, GS, F, Huz, vhf, FG, T1, T2, Ct, D, Dold, evals, eigwork, red_part, red_out,
+  DBuf<double> S, Xh, hcore, heff, GS, F, Huz, vhf, FG, T1, T2, Ct, D, Dold, evals, eigwork, eigwork2, red_part, red_out,
       Corth, Ssave, dm0f;
   DBuf<int> devinfo;
   DiisState diis;
   // subspace (Chebyshev-filtered) tracking of the occupied block between full eigensolves
   int eig_mode = 1;  // 0: cuSOLVER every cycle; 1: filtered subspace iteration when eligible (cuSOLVER first / last / fallback)
   bool sub_valid = false;
+  int sub_min_nao = 256;  // below this the library eigensolver is cheaper than tracking a 16/32-vector block
   bool last_eig_full = true;
   int sub_kb = 0;
   long sub_applies = 0, sub_fallbacks = 0, sub_outer = 0;
@@ -602,12 +603,36 @@ static void eigh_batched(nbd_ctx* c, double* A, double* w, int n, int batch) {
   int* info = c->devinfo.ensure(8);
   NBD_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 8, c->stream));
   const bool dist = eig_distributed(c, batch);
+  // single rank, two spins: the second solve is issued from a helper thread on the side stream.  dsyevd blocks its
+  // calling thread on internal synchronisations, so only two issuing threads let the two solves overlap
+  // (35.2 -> 30.8 ms at n = 1376, profiles/eig_bench_r01.log)
+  const bool two_threads = !dist && batch == 2 && c->overlap && n >= 512;
   {
     StageScope ts(c->timers, c->stream, "eigh");
+    std::future<cusolverStatus_t> side;
+    if (two_threads) {
+      double* work2 = c->eigwork2.ensure((size_t)lwork);
+      NBD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+      NBD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+      const int dev_id = c->device;
+      cusolverDnHandle_t h2 = c->solver2;
+      double* A2 = A + (long)n * n;
+      double* w2 = w + n;
+      side = std::async(std::launch::async, [=] {
+        cudaSetDevice(dev_id);
+        return cusolverDnDsyevd(h2, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A2, n, w2, work2, lwork, info + 1);
+      });
+    }
     for (int b = 0; b < batch; ++b) {
-      if (dist && b != c->rank) continue;
+      if ((dist && b != c->rank) || (two_threads && b == 1)) continue;
       NBD_SOLVER(cusolverDnDsyevd(c->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A + (long)b * n * n, n,
                                   w + (long)b * n, work, lwork, info + b));
+    }
+    if (two_threads) {
+      const cusolverStatus_t st2 = side.get();
+      NBD_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+      NBD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+      if (st2 != CUSOLVER_STATUS_SUCCESS) fail(NBD_ERR_CUDA, "cusolverDnDsyevd (side stream): status %d", (int)st2);
     }
   }
   if (dist) eig_exchange(c, A, w, n);
@@ -795,6 +820,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "panel_stages") c->panel_stages = (int)value;
   else if (k == "jpass_variant") c->jpass_variant = (int)value;
   else if (k == "eig_mode") { c->eig_mode = (int)value; c->sub_valid = false; }
+  else if (k == "sub_min_nao") { c->sub_min_nao = (int)value; c->sub_valid = false; }
   else return NBD_ERR_ARG;
   return NBD_OK;
 }

@@ -5,7 +5,7 @@
 static int sub_block_size(const nbd_ctx* c) {
   int omax = 0;
   for (int s = 0; s < c->nspin; ++s) omax = std::max(omax, c->nspin == 2 ? c->nelec[s] : (c->nelec[0] + c->nelec[1]) / 2);
-  if (c->eig_mode != 1 || c->projector != NBD_HUZINAGA || c->nao < 256 || omax < 1) return 0;
+  if (c->eig_mode != 1 || c->projector != NBD_HUZINAGA || c->nao < c->sub_min_nao || omax < 1) return 0;
   if (omax <= 10) return 16;
   if (omax <= 24) return 32;
   return 0;

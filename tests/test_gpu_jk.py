@@ -98,3 +98,27 @@ def test_jk_empty_inputs(ctx):
     rj, rk = ps.df_get_jk_occ(b, [np.zeros((n, 0)), np.ones((n, 1)) / n])
     assert np.abs(vj - rj).max() < 1e-13 and np.abs(vk - rk).max() < 1e-13
     assert not vk[0].any() and not vj[0].any()
+
+
+def test_jk_and_ao2mo_fuzz_small_shapes(ctx):
+    """Seeded sweep over awkward shapes: tile-boundary AO counts, tiny aux ranges, empty / full / unequal orbital sets."""
+    from oracle import nbed_restatement as nr
+
+    rng = np.random.default_rng(2024)
+    shapes = [(1, 1), (2, 3), (31, 2), (32, 5), (33, 4), (63, 3), (64, 2), (65, 7), (96, 1), (97, 3), (129, 2), (255, 2),
+              (256, 3), (257, 2)]
+    for n, naux in shapes:
+        b = rng.normal(size=(naux, n * (n + 1) // 2)) / n
+        ctx.load_cderi(b)
+        for nocc in {(min(n, 1), 0), (min(n, 3), min(n, 2)), (min(n, 9), min(n, 16))}:
+            orbs = [rng.normal(size=(n, o)) / np.sqrt(n) for o in nocc]
+            vj, vk = ctx.jk_orbitals(orbs)
+            rj, rk = ps.df_get_jk_occ(b, orbs)
+            scale = max(1.0, np.abs(rj).max(), np.abs(rk).max())
+            assert np.abs(vj - rj).max() <= 1e-12 * scale, (n, naux, nocc)
+            assert np.abs(vk - rk).max() <= 1e-12 * scale, (n, naux, nocc)
+        m = min(n, 5)
+        c = rng.normal(size=(2, n, m)) / np.sqrt(n)
+        got = ctx.ao2mo(c[0], c[1])
+        want = nr.two_body_integrals(b, c, restricted=False)
+        assert np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), (n, naux)
