@@ -15,43 +15,42 @@
 
 namespace nbd {
 
-constexpr int SUB_ROWS = 64;    // output rows per CTA (4 warps x 16 rows)
-constexpr int SUB_JCHUNK = 32;  // contraction chunk per pipeline stage
-constexpr int SUB_MAX_SPLIT = 16;
+constexpr int SUB_ROWS = 16;    // output rows per CTA
+constexpr int SUB_JCHUNK = 64;  // contraction chunk per pipeline stage (16 per warp)
+constexpr int SUB_STAGES = 4;
 
 struct SubApplyArgs {
   const double* A;  // [batch][n][n] symmetric
   const double* Y;  // [batch][n][KB]
   const double* Z;  // [batch][n][KB] or null
   double* out;      // [batch][n][KB]
-  double* part;     // [batch][nsplit][n][KB] workspace
-  unsigned int* ticket;  // [batch][row blocks]
-  int n, nsplit;
+  int n;
   double alpha[2], shift[2], beta[2];  // per batch entry: out = alpha * (A Y - shift Y) - beta Z
 };
 
 template <int KB>
 constexpr int sub_apply_smem_bytes() {
-  return (2 * SUB_ROWS * (SUB_JCHUNK + 4) + 2 * SUB_JCHUNK * (KB + 4)) * 8;
+  return SUB_STAGES * (SUB_ROWS * (SUB_JCHUNK + 4) + SUB_JCHUNK * (KB + 4)) * 8;
 }
 
-// out = alpha (A Y - shift Y) - beta Z.  FP64 tensor-core (DMMA m8n8k4) skinny product: a CTA owns 64 rows and a
-// slice of the contraction index (split-K over `nsplit` CTAs per row block, two-stage cp.async ring); the last
-// CTA to finish a row block sums the partials in index order (deterministic) and applies the epilogue.
+// out = alpha (A Y - shift Y) - beta Z.  FP64 tensor-core (DMMA m8n8k4) skinny product over L2-resident data: a CTA
+// owns 16 rows and the whole contraction index, streamed through a 4-stage cp.async ring in chunks of 64; its four
+// warps take 16 contraction indices of every chunk each and their partial tiles are summed through shared memory in
+// warp order (deterministic).  No inter-CTA reduction, so one step is one short launch.
 template <int KB>
 __global__ void __launch_bounds__(128) sub_apply_kernel(SubApplyArgs a) {
   constexpr int A_LD = SUB_JCHUNK + 4, Y_LD = KB + 4, NI = KB / 8;
+  constexpr int A_ST = SUB_ROWS * A_LD, Y_ST = SUB_JCHUNK * Y_LD;
   extern __shared__ __align__(16) double sub_smem[];
-  double(*As)[SUB_ROWS * A_LD] = reinterpret_cast<double(*)[SUB_ROWS * A_LD]>(sub_smem);
-  double(*Ys)[SUB_JCHUNK * Y_LD] = reinterpret_cast<double(*)[SUB_JCHUNK * Y_LD]>(sub_smem + 2 * SUB_ROWS * A_LD);
-  __shared__ unsigned int is_last;
-  const int rb = blockIdx.x, sp = blockIdx.y, b = blockIdx.z;
+  double* As = sub_smem;
+  double* Ys = sub_smem + SUB_STAGES * A_ST;
+  const int rb = blockIdx.x, b = blockIdx.z;
   const int n = a.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, tq = lane & 3;
   const double* A = a.A + (long)b * n * n;
   const double* Y = a.Y + (long)b * n * KB;
   const int nchunk = (n + SUB_JCHUNK - 1) / SUB_JCHUNK;
-  const int c0 = (int)((long)nchunk * sp / a.nsplit), c1 = (int)((long)nchunk * (sp + 1) / a.nsplit);
+  const bool vec = (n & 1) == 0;  // rows of A start 16-byte aligned
   double acc[2][NI][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -59,34 +58,53 @@ __global__ void __launch_bounds__(128) sub_apply_kernel(SubApplyArgs a) {
     for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   auto load = [&](int ch, int buf) {
     const int j0 = ch * SUB_JCHUNK;
+    double* as = As + buf * A_ST;
+    double* ys = Ys + buf * Y_ST;
+    if (vec) {
 #pragma unroll
-    for (int q = 0; q < SUB_ROWS * SUB_JCHUNK / 128; ++q) {
-      const int e = tid + 128 * q;
-      const int r = e / SUB_JCHUNK, j = e % SUB_JCHUNK;
-      const int gi = rb * SUB_ROWS + r, gj = j0 + j;
-      const bool ok = gi < n && gj < n;
-      cp_async8(&As[buf][r * A_LD + j], ok ? A + (long)gi * n + gj : A, ok);
+      for (int q = 0; q < SUB_ROWS * SUB_JCHUNK / 2 / 128; ++q) {
+        const int e = tid + 128 * q;
+        const int r = e / (SUB_JCHUNK / 2), j = 2 * (e % (SUB_JCHUNK / 2));
+        const int gi = rb * SUB_ROWS + r, gj = j0 + j;
+        const bool ok = gi < n && gj < n;  // n even: a pair never straddles the edge
+        cp_async16(as + r * A_LD + j, ok ? A + (long)gi * n + gj : A, ok);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < SUB_ROWS * SUB_JCHUNK / 128; ++q) {
+        const int e = tid + 128 * q;
+        const int r = e / SUB_JCHUNK, j = e % SUB_JCHUNK;
+        const int gi = rb * SUB_ROWS + r, gj = j0 + j;
+        const bool ok = gi < n && gj < n;
+        cp_async8(as + r * A_LD + j, ok ? A + (long)gi * n + gj : A, ok);
+      }
     }
 #pragma unroll
-    for (int q = 0; q < SUB_JCHUNK * KB / 128; ++q) {
+    for (int q = 0; q < SUB_JCHUNK * KB / 2 / 128; ++q) {
       const int e = tid + 128 * q;
-      const int j = e / KB, c = e % KB;
+      const int j = e / (KB / 2), c2 = 2 * (e % (KB / 2));
       const bool ok = j0 + j < n;
-      cp_async8(&Ys[buf][j * Y_LD + c], ok ? Y + (long)(j0 + j) * KB + c : Y, ok);
+      cp_async16(ys + j * Y_LD + c2, ok ? Y + (long)(j0 + j) * KB + c2 : Y, ok);
     }
   };
-  if (c0 < c1) load(c0, 0);
-  cp_async_commit();
-  for (int ch = c0; ch < c1; ++ch) {
-    const int buf = (ch - c0) & 1;
-    if (ch + 1 < c1) load(ch + 1, buf ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    const double* as = &As[buf][(16 * warp + gq) * A_LD + tq];
-    const double* ys = &Ys[buf][tq * Y_LD + gq];
 #pragma unroll
-    for (int k4 = 0; k4 < SUB_JCHUNK; k4 += 4) {
+  for (int s = 0; s < SUB_STAGES - 1; ++s) {
+    if (s < nchunk) load(s, s);
+    cp_async_commit();
+  }
+  for (int ch = 0; ch < nchunk; ++ch) {
+    cp_async_wait<SUB_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nx = ch + SUB_STAGES - 1;
+      if (nx < nchunk) load(nx, nx % SUB_STAGES);
+      cp_async_commit();
+    }
+    const int buf = ch % SUB_STAGES;
+    const double* as = As + buf * A_ST + gq * A_LD + 16 * warp + tq;
+    const double* ys = Ys + buf * Y_ST + (16 * warp + tq) * Y_LD + gq;
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
       double af[2], bf[NI];
       af[0] = as[k4];
       af[1] = as[8 * A_LD + k4];
@@ -97,64 +115,31 @@ __global__ void __launch_bounds__(128) sub_apply_kernel(SubApplyArgs a) {
 #pragma unroll
         for (int j = 0; j < NI; ++j) dmma(acc[i][j], af[i], bf[j]);
     }
-    __syncthreads();
   }
   cp_async_wait<0>();
-  double* part = a.part + (((long)b * a.nsplit + sp) * n) * KB;
+  __syncthreads();
+  // sum the four warps' partial 16 x KB tiles through shared memory (fixed order), then the epilogue
+  double* red = sub_smem;  // [4][16][KB]
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int gi = rb * SUB_ROWS + 16 * warp + 8 * i + gq;
-    if (gi < n) {
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < NI; ++j)
-        *reinterpret_cast<double2*>(&part[(long)gi * KB + 8 * j + 2 * tq]) = make_double2(acc[i][j][0], acc[i][j][1]);
+    for (int j = 0; j < NI; ++j) {
+      double* p = red + ((warp * 16) + 8 * i + gq) * KB + 8 * j + 2 * tq;
+      p[0] = acc[i][j][0];
+      p[1] = acc[i][j][1];
     }
-  }
-  __threadfence();
   __syncthreads();
-  if (tid == 0) {
-    const unsigned int t = atomicAdd(&a.ticket[b * gridDim.x + rb], 1u);
-    is_last = (t == (unsigned int)a.nsplit - 1) ? 1u : 0u;
-    if (is_last) a.ticket[b * gridDim.x + rb] = 0u;  // re-arm for the next launch
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
   const double alpha = a.alpha[b], shift = a.shift[b], beta = a.beta[b];
   const double* Z = a.Z ? a.Z + (long)b * n * KB : nullptr;
   double* out = a.out + (long)b * n * KB;
-  // epilogue of the row block: SUB_ROWS * KB outputs, all partial loads of a thread issued independently
-  constexpr int OPT = SUB_ROWS * KB / 128;  // outputs per thread
-  double s[OPT];
-  long off[OPT];
-  bool ok[OPT];
-#pragma unroll
-  for (int q = 0; q < OPT; ++q) {
-    const int e = tid + 128 * q;
+  for (int e = tid; e < SUB_ROWS * KB; e += 128) {
     const int gi = rb * SUB_ROWS + e / KB;
-    ok[q] = gi < n;
-    off[q] = (long)min(gi, n - 1) * KB + e % KB;
-    s[q] = 0.0;
-  }
-  const long pstride = (long)n * KB;
-  const double* pbase = a.part + (long)b * a.nsplit * pstride;
-  for (int k = 0; k < a.nsplit; k += 2) {
-    double v0[OPT], v1[OPT];
-    const bool two = k + 1 < a.nsplit;
-#pragma unroll
-    for (int q = 0; q < OPT; ++q) {
-      v0[q] = __ldcg(pbase + k * pstride + off[q]);
-      v1[q] = two ? __ldcg(pbase + (k + 1) * pstride + off[q]) : 0.0;
-    }
-#pragma unroll
-    for (int q = 0; q < OPT; ++q) s[q] = (s[q] + v0[q]) + v1[q];
-  }
-#pragma unroll
-  for (int q = 0; q < OPT; ++q) {
-    if (!ok[q]) continue;
-    double v = alpha * (s[q] - shift * Y[off[q]]);
-    if (Z) v -= beta * Z[off[q]];
-    out[off[q]] = v;
+    if (gi >= n) continue;
+    const double s = ((red[e] + red[16 * KB + e]) + red[2 * 16 * KB + e]) + red[3 * 16 * KB + e];
+    const long o = (long)gi * KB + e % KB;
+    double v = alpha * (s - shift * Y[o]);
+    if (Z) v -= beta * Z[o];
+    out[o] = v;
   }
 }
 

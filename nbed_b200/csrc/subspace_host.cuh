@@ -14,7 +14,6 @@ static int sub_block_size(const nbd_ctx* c) {
 static void sub_alloc(nbd_ctx* c, int kb) {
   const size_t blk = (size_t)2 * c->nao * kb;
   for (DBuf<double>* b : {&c->sV, &c->sY, &c->sZ, &c->sW, &c->sAV}) b->ensure(blk);
-  c->sPart.ensure(blk * SUB_MAX_SPLIT);
   c->sG.ensure((size_t)2 * 2 * kb * kb);
   c->sGpart.ensure((size_t)2 * 64 * 2 * kb * kb);
   c->sM.ensure((size_t)2 * kb * kb);
@@ -51,15 +50,13 @@ static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double
                       const double* shift, const double* beta) {
   const int n = c->nao;
   SubApplyArgs a{};
-  a.A = A; a.Y = Y; a.Z = Z; a.out = out; a.part = c->sPart.p; a.ticket = c->sTicket.p;
+  a.A = A; a.Y = Y; a.Z = Z; a.out = out;
   a.n = n;
   const int nrb = (n + SUB_ROWS - 1) / SUB_ROWS;
-  // latency-bound kernel over L2-resident data: many short CTAs (about 4-5 per SM) beat few long ones
-  a.nsplit = std::max(1, std::min(SUB_MAX_SPLIT, (3 * c->sm_count) / std::max(1, nrb * c->nspin)));
   for (int b = 0; b < 2; ++b) {
     a.alpha[b] = alpha[b]; a.shift[b] = shift[b]; a.beta[b] = beta[b];
   }
-  dim3 g(nrb, a.nsplit, c->nspin);
+  dim3 g(nrb, 1, c->nspin);
   constexpr int smem = sub_apply_smem_bytes<KB>();
   static bool attr_set = false;
   if (!attr_set) {
