@@ -239,6 +239,8 @@ extern "C" int nbd_scf_setup(nbd_ctx* c, int nspin, const int* nelec, const doub
     LAUNCH_CHECK(c);
     c->scf_ready = true;
     c->bench_ready = false;
+    c->sub_valid = false;  // a tracked eigenvector block never survives a change of problem
+    c->last_eig_full = true;
     finish_call(c);
   });
 }
@@ -316,6 +318,8 @@ extern "C" int nbd_huzinaga_scf(nbd_ctx* c, int max_cycle, double conv_tol, doub
     {
     StageScope ts_all(c->timers, c->stream, "scf_total");
     HuzLoop L;
+    c->sub_valid = false;  // every SCF run starts from a full diagonalisation (or the caller's density)
+    c->last_eig_full = true;
     huz_initial(c, dm0, L);
     c->diis.init(6, c->nspin * nn, false);
     double eprev[2] = {0.0, 0.0}, e[2] = {0.0, 0.0}, nd = 0.0;
