@@ -36,12 +36,16 @@ int nbd_version(void);
 int nbd_create(nbd_ctx** out, int device);
 int nbd_destroy(nbd_ctx* ctx);
 const char* nbd_last_error(nbd_ctx* ctx);
-/* Tuning / debugging knobs ("jk_variant": 0 = DMMA pipeline, 1 = simple reference kernels;
- * "gemm_variant": 0 = DMMA tiles, 1 = simple).  Returns NBD_ERR_ARG for an unknown key. */
+/* Tuning / debugging knobs (listed with nbd_timer_ms below).  Returns NBD_ERR_ARG for an unknown key. */
 int nbd_set_option(nbd_ctx* ctx, const char* key, long value);
 /* Per-stage device timings (CUDA events) of the last call, in milliseconds.
- * keys: "jk_x", "jk_rho", "jk_j", "jk_k", "jk_total", "allreduce", "fock", "diis", "orth", "eigh",
- *       "density", "energy", "ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_total", "iter_total".   */
+ * keys: "jk_x" (pass 1), "jk_rho", "jk_j" (pass 2), "jk_k" (Gram), "jk_total", "allreduce", "fock", "diis", "orth",
+ *       "eigh" (cuSOLVER), "eig_sub" (filtered subspace iteration), "eig_bcast", "density", "energy", "iter_total",
+ *       "scf_total", "ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm", "ao2mo_total", "spinorb", "build_total".
+ * Cumulative counters since context creation: "count:sub_applies", "count:sub_outer", "count:sub_fallbacks".
+ * Options of nbd_set_option: "jk_variant", "gemm_variant" (1 = simple reference kernels), "jpass_variant"
+ * (0 = TMA-fed, 1 = LDG streaming), "eig_mode" (0 = cuSOLVER every cycle, 1 = subspace tracking), "sub_min_nao",
+ * "overlap", "dist_eig", "panel_stages", "x_budget_mb", "timers". */
 double nbd_timer_ms(nbd_ctx* ctx, const char* key);
 /* Number of kernels launched by this library since the context was created (bench "gpu_launches"). */
 long nbd_launch_count(nbd_ctx* ctx);

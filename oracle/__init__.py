@@ -20,7 +20,12 @@ Contents
 ``gaussian_integrals`` minimal s/p Gaussian integral generator (libcint is absent) used to rebuild the
                        water/STO-3G system of the reference's tests, so that the oracle can be pinned on
                        the reference's own golden energies (tests/test_driver.py:56-57,76).
-``synthetic``          the shape-synthetic problem generator of SURVEY.md §8(d), shared by tests/bench.
+``c_kernels.c``        plain-C (OpenMP) restatement of the DF-J/K contraction, built by ``oracle/Makefile`` into
+                       ``oracle/_build`` and bound by ``c_binding``; cross-checked against the NumPy restatement.
+``fock_space``         Fock-space matrix and Jordan-Wigner Pauli terms of a second-quantised Hamiltonian (stands in
+                       for openfermion in the builder tests).
+(The shape-synthetic problem generator of SURVEY.md §8(d) lives in ``nbed_b200/synthetic.py``: it is shared by the
+product's benchmark and the tests and contains no reference arithmetic.)
 
 Parity status: PINNED for the pieces listed in DESIGN.md §oracle (reference-run fixtures + the
 water/STO-3G HF/FCI goldens); the DFT-derived known answers of tests/test_scf.py need libxc and remain
