@@ -48,7 +48,7 @@ def _worker(rank, world, port, ret):
 
 def test_aux_sharded_partials_allreduce_to_full_result():
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()  # (fork of a multi-threaded pytest process can deadlock)
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     p = syn.make_problem(n=20, naux=37, nocc=3, n_env=2, seed=2, scale=0.05)
