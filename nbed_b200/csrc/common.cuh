@@ -60,6 +60,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// streaming variant: the 3-centre tensor is read once per pass and is far larger than L2, so its lines are marked
+// evict-first and do not push the reusable operands (X, orbitals, F') out of the cache
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
 // ---- cp.async (LDGSTS) 8-byte with zero fill ----------------------------------------------------
 __device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid) {
   int sz = valid ? 8 : 0;

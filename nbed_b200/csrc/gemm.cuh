@@ -28,7 +28,7 @@ struct GemmArgs {
 };
 
 constexpr int GEMM_BK = 16;
-constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_STAGES = 3;
 
 // A_MC: A tile stored [k][m] (m contiguous in global memory), else [m][k].  B_NC: B tile stored [k][n].
 template <int BM, int BN, int WM, int WN, bool A_MC, bool B_NC>

@@ -290,13 +290,14 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
       int st = 0, fb = 0;
       uint32_t ph = 1;  // parity of the "previous round released" phase; the first round needs no wait
       bool first_round = true;
+      const uint64_t pol = l2_evict_first_policy();
       for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
         const long P = item / p.nslices;
         const double* src = p.Bt + P * (long)p.ntiles * TILE_ELEMS;
         for (int k = 0; k < p.ntiles; ++k) {
           if (!first_round) mbar_wait(&empty[st], ph);
           mbar_expect_tx(&full[fb], TILE_BYTES);
-          bulk_g2s(stages + (size_t)st * TILE_ELEMS, src + (long)k * TILE_ELEMS, TILE_BYTES, &full[fb]);
+          bulk_g2s_stream(stages + (size_t)st * TILE_ELEMS, src + (long)k * TILE_ELEMS, TILE_BYTES, &full[fb], pol);
           if (++fb == 2 * S) fb = 0;
           if (++st == S) {
             st = 0;
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(256) j_pass_kernel(const double2* __restrict__
 // P-range through a ring of 8 KiB bulk copies, four consumer warps accumulate rho[P] * tile in registers.  It keeps
 // ~64 KiB in flight per CTA with 160 threads and 17 registers' worth of accumulators, so it reaches HBM speed next
 // to the tensor-bound K Gram (whose CTAs leave little room for the register-hungry LDG version above).
-constexpr int JP_STAGES = 8;
+constexpr int JP_STAGES = 7;  // 2 CTAs of 57 KiB fit next to one 101 KiB Gram CTA on an SM
 constexpr int JP_THREADS = 160;  // 4 consumer warps + 1 producer warp
 template <int NSET>
 __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __restrict__ Bt, const double* __restrict__ rho,
@@ -512,6 +513,7 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
       int st = 0;
       uint32_t ph = 1;
       bool first = true;
+      const uint64_t pol = l2_evict_first_policy();
       for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int sp = (int)(item / ntiles), k = (int)(item % ntiles);
         const int p0 = sp * rows_per_split, p1 = min(naux, p0 + rows_per_split);
@@ -519,7 +521,7 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
         for (int p = p0; p < p1; ++p, src += (long)ntiles * TILE_ELEMS) {
           if (!first) mbar_wait(&empty[st], ph);
           mbar_expect_tx(&full[st], TILE_BYTES);
-          bulk_g2s(stages + (size_t)st * TILE_ELEMS, src, TILE_BYTES, &full[st]);
+          bulk_g2s_stream(stages + (size_t)st * TILE_ELEMS, src, TILE_BYTES, &full[st], pol);
           if (++st == JP_STAGES) {
             st = 0;
             ph ^= 1u;
