@@ -490,14 +490,20 @@ __global__ void __launch_bounds__(256) j_pass_kernel(const double2* __restrict__
 // to the tensor-bound K Gram (whose CTAs leave little room for the register-hungry LDG version above).
 constexpr int JP_STAGES = 7;  // 2 CTAs of 57 KiB fit next to one 101 KiB Gram CTA on an SM
 constexpr int JP_THREADS = 160;  // 4 consumer warps + 1 producer warp
+// Work items (P-range, tile) are handed out dynamically (one atomic counter): next to the Gram the CTAs of this
+// kernel run at very different speeds depending on what shares their SM, and a static split would wait for the
+// slowest.  The producer lane draws the item, publishes it through shared memory ahead of the item's first tile
+// (the mbarrier completion orders the two), and releases the consumers with a bare arrival when the queue is dry.
 template <int NSET>
 __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __restrict__ Bt, const double* __restrict__ rho,
                                                                 double* __restrict__ part, int ntiles, int naux,
-                                                                int nsplit, int rows_per_split) {
+                                                                int nsplit, int rows_per_split,
+                                                                unsigned int* __restrict__ next_item) {
   extern __shared__ __align__(128) unsigned char jsm[];
   uint64_t* full = reinterpret_cast<uint64_t*>(jsm);
   uint64_t* empty = full + JP_STAGES;
-  double* stages = reinterpret_cast<double*>(jsm + 128);
+  volatile long* item_q = reinterpret_cast<volatile long*>(jsm + 128);  // [8] items in flight (>= ring depth + 1), indexed by sequence & 7
+  double* stages = reinterpret_cast<double*>(jsm + 256);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < JP_STAGES; ++s) {
@@ -507,19 +513,27 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
     mbar_fence_init();
   }
   __syncthreads();
-  const long nitems = (long)ntiles * nsplit;  // item = (split, tile): consecutive CTAs take consecutive tiles
+  const long nitems = (long)ntiles * nsplit;  // item = (split, tile): consecutive items are consecutive tiles
   if (warp == 4) {
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 1;
       bool first = true;
       const uint64_t pol = l2_evict_first_policy();
-      for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+      for (unsigned int seq = 0;; ++seq) {
+        long item = (long)atomicAdd(next_item, 1u);
+        if (item >= nitems) item = -1;
+        if (!first) mbar_wait(&empty[st], ph);  // (also guarantees the consumers are done with item_q[seq & 7])
+        item_q[seq & 7] = item;
+        if (item < 0) {
+          mbar_arrive(&full[st]);  // nothing to copy: release the consumers, which then read the sentinel
+          break;
+        }
         const int sp = (int)(item / ntiles), k = (int)(item % ntiles);
         const int p0 = sp * rows_per_split, p1 = min(naux, p0 + rows_per_split);
         const double* src = Bt + ((long)p0 * ntiles + k) * TILE_ELEMS;
         for (int p = p0; p < p1; ++p, src += (long)ntiles * TILE_ELEMS) {
-          if (!first) mbar_wait(&empty[st], ph);
+          if (p > p0 && !first) mbar_wait(&empty[st], ph);
           mbar_expect_tx(&full[st], TILE_BYTES);
           bulk_g2s_stream(stages + (size_t)st * TILE_ELEMS, src, TILE_BYTES, &full[st], pol);
           if (++st == JP_STAGES) {
@@ -534,7 +548,10 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
   }
   const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
   uint32_t st = 0, ph = 0;
-  for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+  for (unsigned int seq = 0;; ++seq) {
+    mbar_wait_a(full_a + 8u * st, ph);  // first tile of the item (or the bare arrival of the sentinel)
+    const long item = item_q[seq & 7];
+    if (item < 0) break;
     const int sp = (int)(item / ntiles), k = (int)(item % ntiles);
     const int p0 = sp * rows_per_split, p1 = min(naux, p0 + rows_per_split);
     double2 acc[NSET][4];
@@ -546,7 +563,7 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
       double r[NSET];
 #pragma unroll
       for (int s = 0; s < NSET; ++s) r[s] = __ldg(rho + (long)s * naux + p);
-      mbar_wait_a(full_a + 8u * st, ph);
+      if (p > p0) mbar_wait_a(full_a + 8u * st, ph);
       const double2* t2 = reinterpret_cast<const double2*>(stages + (size_t)st * TILE_ELEMS);
       double2 v[4];
 #pragma unroll

@@ -225,6 +225,7 @@ struct nbd_ctx {
   PanelPlan plan;
   DBuf<uint32_t> d_events;
   DBuf<int> d_evbegin;
+  DBuf<unsigned int> d_jcounter;
   DBuf<long> d_xtab;  // group-major layout tables of the half-transformed tensor: [xbase | xstride]
 
   // ---- SCF problem ----
@@ -457,21 +458,13 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
     const long E = (long)c->ntiles * TILE_ELEMS, E2 = E / 2;
     dim3 gf((n + 127) / 128, n);
     if (c->jpass_variant == 0) {
-      // TMA-fed persistent kernel: items = (P-range, tile); pick the split that balances the static round-robin
+      // TMA-fed persistent kernel: items = (P-range, tile), drawn dynamically; ~16 items per CTA keep the tail short
       const int ctas = 2 * c->sm_count;
-      int nsplit = 1;
-      double best = 1e30;
-      for (int sp = 1; sp <= std::min(naux, 8); ++sp) {
-        const long items = (long)c->ntiles * sp;
-        const double rounds = std::ceil((double)items / ctas), cost = rounds / sp;  // time ~ rounds * rows per item
-        if (cost < best * 0.999) {
-          best = cost;
-          nsplit = sp;
-        }
-      }
+      int nsplit = (int)std::max<long>(1, std::min<long>(std::min(naux, 16), (16L * ctas + c->ntiles - 1) / c->ntiles));
       const int rows_per_split = (naux + nsplit - 1) / nsplit;
       nsplit = (naux + rows_per_split - 1) / rows_per_split;
-      const size_t smem = 128 + (size_t)JP_STAGES * TILE_BYTES;
+      unsigned int* counter = c->d_jcounter.ensure(4);
+      const size_t smem = 256 + (size_t)JP_STAGES * TILE_BYTES;
       static bool attr_set = false;
       if (!attr_set) {
         NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -482,10 +475,11 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
         const int ns = std::min(2, njset - s0);
         double* part = c->d_jpart.ensure((size_t)nsplit * ns * E);
         const int grid = (int)std::min<long>((long)c->ntiles * nsplit, ctas);
+        NBD_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
         if (ns == 2)
-          j_pass_tma_kernel<2><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split);
+          j_pass_tma_kernel<2><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter);
         else
-          j_pass_tma_kernel<1><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split);
+          j_pass_tma_kernel<1><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter);
         LAUNCH_CHECK(c);
         j_finalize_kernel<<<gf, 128, 0, st>>>(part, c->d_inv.p, d_J + (long)s0 * nn, n, c->nb, E, nsplit, ns);
         LAUNCH_CHECK(c);
