@@ -489,7 +489,9 @@ __global__ void __launch_bounds__(256) j_pass_kernel(const double2* __restrict__
 // ~64 KiB in flight per CTA with 160 threads and 17 registers' worth of accumulators, so it reaches HBM speed next
 // to the tensor-bound K Gram (whose CTAs leave little room for the register-hungry LDG version above).
 constexpr int JP_STAGES = 7;  // 2 CTAs of 57 KiB fit next to one 101 KiB Gram CTA on an SM
-constexpr int JP_THREADS = 160;  // 4 consumer warps + 1 producer warp
+constexpr int JP_CONSUMERS = 4;    // consumer warps (8 lighter warps were measured slower next to the Gram)
+constexpr int JP_THREADS = (JP_CONSUMERS + 1) * 32;
+constexpr int JP_Q = 512 / (JP_CONSUMERS * 32);  // double2 per thread per tile
 // Work items (P-range, tile) are handed out dynamically (one atomic counter): next to the Gram the CTAs of this
 // kernel run at very different speeds depending on what shares their SM, and a static split would wait for the
 // slowest.  The producer lane draws the item, publishes it through shared memory ahead of the item's first tile
@@ -508,13 +510,13 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
   if (tid == 0) {
     for (int s = 0; s < JP_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 4);
+      mbar_init(&empty[s], JP_CONSUMERS);
     }
     mbar_fence_init();
   }
   __syncthreads();
   const long nitems = (long)ntiles * nsplit;  // item = (split, tile): consecutive items are consecutive tiles
-  if (warp == 4) {
+  if (warp == JP_CONSUMERS) {
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 1;
@@ -554,26 +556,26 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
     if (item < 0) break;
     const int sp = (int)(item / ntiles), k = (int)(item % ntiles);
     const int p0 = sp * rows_per_split, p1 = min(naux, p0 + rows_per_split);
-    double2 acc[NSET][4];
+    double2 acc[NSET][JP_Q];
 #pragma unroll
     for (int s = 0; s < NSET; ++s)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[s][q] = make_double2(0.0, 0.0);
+      for (int q = 0; q < JP_Q; ++q) acc[s][q] = make_double2(0.0, 0.0);
     for (int p = p0; p < p1; ++p) {
       double r[NSET];
 #pragma unroll
       for (int s = 0; s < NSET; ++s) r[s] = __ldg(rho + (long)s * naux + p);
       if (p > p0) mbar_wait_a(full_a + 8u * st, ph);
       const double2* t2 = reinterpret_cast<const double2*>(stages + (size_t)st * TILE_ELEMS);
-      double2 v[4];
+      double2 v[JP_Q];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = t2[tid + 128 * q];
+      for (int q = 0; q < JP_Q; ++q) v[q] = t2[tid + JP_CONSUMERS * 32 * q];
       __syncwarp();
       if (lane == 0) mbar_arrive_a(empty_a + 8u * st);
 #pragma unroll
       for (int s = 0; s < NSET; ++s)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < JP_Q; ++q) {
           acc[s][q].x = fma(r[s], v[q].x, acc[s][q].x);
           acc[s][q].y = fma(r[s], v[q].y, acc[s][q].y);
         }
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
     for (int s = 0; s < NSET; ++s) {
       double2* o = reinterpret_cast<double2*>(part + (((long)sp * NSET + s) * ntiles + k) * TILE_ELEMS);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) o[tid + 128 * q] = acc[s][q];
+      for (int q = 0; q < JP_Q; ++q) o[tid + JP_CONSUMERS * 32 * q] = acc[s][q];
     }
   }
 }
