@@ -196,6 +196,7 @@ struct nbd_ctx {
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
   int overlap = 1;
   int dist_eig = 1;
+  int gemm_tile = 0;      // tuning: force the GEMM tile size (0 = heuristic)
   int jpass_variant = 0;  // 0: TMA-fed persistent pass 2, 1: LDG streaming pass 2
   int panel_stages = 0;  // tuning: cap on the ring depth of the panel kernel (0 = as many as fit)  // distribute the two spins' eigensolves over ranks 0 / 1 when a communicator exists
   std::string err;
@@ -275,7 +276,7 @@ static void gemm(nbd_ctx* c, int M, int N, int K, const double* A, long a_is, lo
   g.B = B; g.b_js = b_js; g.b_ks = b_ks;
   g.C = C; g.ldc = ldc; g.alpha = alpha; g.beta = beta;
   g.batch = batch; g.strideA = sA; g.strideB = sB; g.strideC = sC; g.lower_only = lower;
-  NBD_CUDA(launch_gemm(c->stream, g, c->gemm_variant, &c->launches, c->sm_count));
+  NBD_CUDA(launch_gemm(c->stream, g, c->gemm_variant, &c->launches, c->sm_count, c->gemm_tile));
 }
 // C[M][N] = alpha * A[M][K] * B[K][N] + beta * C   (all row-major, leading dimensions given)
 static void gemm_nn(nbd_ctx* c, int M, int N, int K, const double* A, long lda, const double* B, long ldb, double* C,
@@ -813,6 +814,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "dist_eig") c->dist_eig = (int)value;
   else if (k == "panel_stages") c->panel_stages = (int)value;
   else if (k == "jpass_variant") c->jpass_variant = (int)value;
+  else if (k == "gemm_tile") c->gemm_tile = (int)value;
   else if (k == "eig_mode") { c->eig_mode = (int)value; c->sub_valid = false; }
   else if (k == "sub_min_nao") { c->sub_min_nao = (int)value; c->sub_valid = false; }
   else return NBD_ERR_ARG;
