@@ -96,6 +96,11 @@ int nbd_jk_dm(nbd_ctx* ctx, int nset, const double* dm, double* vj, double* vk);
 int nbd_scf_setup(nbd_ctx* ctx, int nspin, const int* nelec, const double* ovlp, const double* hcore,
                   const double* v_emb, const double* dm_env, int projector, double mu);
 
+/* Optional virtual-orbital environment projector of huzinaga_scf (argument dm_environment_virtual,
+ * nbed/scf/huzinaga_scf.py:96,133-136 and the second term of get_huzinaga_operator :82-88; built by the PAO
+ * localizer in nbed/driver.py:566-575).  dm_env_virt [nspin][nao][nao], NULL switches it off.  After nbd_scf_setup. */
+int nbd_scf_set_virtual_projector(nbd_ctx* ctx, const double* dm_env_virt);
+
 typedef struct nbd_scf_result {
   int converged;      /* conv flag                                              */
   int cycles;         /* number of Fock builds executed in the loop             */

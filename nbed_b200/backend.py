@@ -141,6 +141,12 @@ class B200Context:
         self._ck(self._lib.nbd_scf_setup(self._h, nspin, ptr(ne), ptr(f64(ovlp)), ptr(f64(hcore)), ptr(v_emb),
                                          ptr(dm_env), int(projector), float(mu)))
 
+    def scf_set_virtual_projector(self, dm_env_virt):
+        n, ns = self.nao, self._nspin
+        shape = (n, n) if ns == 1 else (2, n, n)
+        d = None if dm_env_virt is None else f64(np.asarray(dm_env_virt).reshape(shape))
+        self._ck(self._lib.nbd_scf_set_virtual_projector(self._h, ptr(d)))
+
     def huzinaga_scf(self, max_cycle, conv_tol, dm_conv_tol=1e-6, use_diis=True, dm0=None):
         n, ns = self.nao, self._nspin
         shape = (n, n) if ns == 1 else (2, n, n)

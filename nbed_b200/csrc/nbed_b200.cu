@@ -231,10 +231,11 @@ struct nbd_ctx {
 
   // ---- SCF problem ----
   bool scf_ready = false;
+  bool have_virt = false;  // virtual-orbital Huzinaga projector present (gamma_virt S in GSv)
   int nspin = 0, projector = 0;
   int nelec[2] = {0, 0};
   double mu = 0.0;
-  DBuf<double> S, Xh, hcore, heff, GS, F, Huz, vhf, FG, T1, T2, Ct, D, Dold, evals, eigwork, eigwork2, red_part, red_out,
+  DBuf<double> S, Xh, hcore, heff, GS, GSv, F, Huz, vhf, FG, T1, T2, Ct, D, Dold, evals, eigwork, eigwork2, red_part, red_out,
       Corth, Ssave, dm0f;
   DBuf<int> devinfo;
   DiisState diis;

@@ -53,8 +53,16 @@ static void scf_apply_huzinaga(nbd_ctx* c) {
   const int n = c->nao;
   const long nn = (long)n * n;
   gemm_nn(c, n, n, n, c->F.p, n, c->GS.p, n, c->FG.p, n, 1.0, 0.0, c->nspin, nn, nn, nn);
+  const double* FGv = nullptr;
+  const double* W = nullptr;
+  if (c->have_virt) {  // virtual-orbital projector (huzinaga_scf.py:82-88): FGv = F GSv, W = GSv^T FGv
+    gemm_nn(c, n, n, n, c->F.p, n, c->GSv.p, n, c->T1.p, n, 1.0, 0.0, c->nspin, nn, nn, nn);
+    gemm_tn(c, n, n, n, c->GSv.p, n, c->T1.p, n, c->T2.p, n, 1.0, 0.0, c->nspin, nn, nn, nn);
+    FGv = c->T1.p;
+    W = c->T2.p;
+  }
   dim3 g((n + 31) / 32, (n + 31) / 32, c->nspin), b(32, 8);
-  huzinaga_apply_kernel<<<g, b, 0, c->stream>>>(c->FG.p, c->nspin == 2 ? 1.0 : 0.5, c->Huz.p, c->F.p, n);
+  huzinaga_apply_kernel<<<g, b, 0, c->stream>>>(c->FG.p, FGv, W, c->nspin == 2 ? 1.0 : 0.5, c->Huz.p, c->F.p, n);
   LAUNCH_CHECK(c);
 }
 
@@ -239,8 +247,28 @@ extern "C" int nbd_scf_setup(nbd_ctx* c, int nspin, const int* nelec, const doub
     LAUNCH_CHECK(c);
     c->scf_ready = true;
     c->bench_ready = false;
+    c->have_virt = false;
     c->sub_valid = false;  // a tracked eigenvector block never survives a change of problem
     c->last_eig_full = true;
+    finish_call(c);
+  });
+}
+
+// Optional virtual-orbital environment projector of huzinaga_scf (dm_environment_virtual, huzinaga_scf.py:133-136,
+// 82-88): dm_env_virt [nspin][nao][nao]; null or all-zero switches it off.  Call after nbd_scf_setup.
+extern "C" int nbd_scf_set_virtual_projector(nbd_ctx* c, const double* dm_env_virt) {
+  return guarded(c, [&] {
+    NBD_REQUIRE(c->scf_ready && c->projector == NBD_HUZINAGA, NBD_ERR_STATE, "nbd_scf_setup(projector = NBD_HUZINAGA) first");
+    const int n = c->nao;
+    const long nn = (long)n * n;
+    c->have_virt = false;
+    if (dm_env_virt) {
+      c->GSv.ensure((size_t)2 * nn);
+      h2d(c, c->T2.p, dm_env_virt, (size_t)c->nspin * nn);
+      gemm_nn(c, n, n, n, c->T2.p, n, c->S.p, n, c->GSv.p, n, 1.0, 0.0, c->nspin, nn, 0, nn);  // gamma_virt S  (:134)
+      c->have_virt = true;
+    }
+    c->bench_ready = false;
     finish_call(c);
   });
 }

@@ -38,23 +38,33 @@ __global__ void add_kernel(const double* __restrict__ a, const double* __restric
   if (i < cnt) out[i] = a[i] + b[i];
 }
 
-// Huz_s = -c (FG_s + FG_s^T);  F_s += Huz_s      (nbed/scf/huzinaga_scf.py:78-80,160)
-__global__ void huzinaga_apply_kernel(const double* __restrict__ FG, double c, double* __restrict__ huz,
+// Huz_s = -c (FG_s + FG_s^T) [ -c (FGv_s + FGv_s^T - 2 W_s) ];  F_s += Huz_s      (nbed/scf/huzinaga_scf.py:78-90,160)
+// FG = F (gamma_occ S); optional virtual-projector part: FGv = F (gamma_virt S), W = (gamma_virt S)^T FGv.
+__global__ void huzinaga_apply_kernel(const double* __restrict__ FG, const double* __restrict__ FGv,
+                                      const double* __restrict__ W, double c, double* __restrict__ huz,
                                       double* __restrict__ F, int n) {
   __shared__ double tile[32][33];
   const long base = (long)blockIdx.z * n * n;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int i = bx + r, j = by + threadIdx.x;  // transposed block: rows from the x-block
-    tile[r][threadIdx.x] = (i < n && j < n) ? FG[base + (long)i * n + j] : 0.0;
+    double v = 0.0;
+    if (i < n && j < n) {
+      v = FG[base + (long)i * n + j];
+      if (FGv) v += FGv[base + (long)i * n + j];
+    }
+    tile[r][threadIdx.x] = v;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int i = by + r, j = bx + threadIdx.x;
     if (i < n && j < n) {
-      const double v = -c * (FG[base + (long)i * n + j] + tile[threadIdx.x][r]);
-      huz[base + (long)i * n + j] = v;
-      F[base + (long)i * n + j] += v;
+      const long e = base + (long)i * n + j;
+      double s = FG[e] + tile[threadIdx.x][r];
+      if (FGv) s += FGv[e] - 2.0 * W[e];
+      const double v = -c * s;
+      huz[e] = v;
+      F[e] += v;
     }
   }
 }

@@ -210,19 +210,22 @@ def huzinaga_scf(scf_method, embedding_potential, dm_environment_occupied, dm_en
     ``(mo_coeff_std, mo_energy, density_matrix, huzinaga_op_std, conv_flag)``.
 
     The whole loop (J/K, Fock, projector, DIIS, orthogonalisation, eigensolve, density, energies, convergence) runs
-    device-resident inside one C-ABI call.  ``dm_environment_virtual`` (the PAO virtual projector) is unreachable
-    from the reference driver (nbed/driver.py:819-820 raises) and is rejected here.
+    device-resident inside one C-ABI call, including the optional virtual-orbital projector
+    ``dm_environment_virtual`` (second term of ``get_huzinaga_operator``, :82-88).
     """
     if not isinstance(scf_method, _B200SCF):
         raise TypeError("huzinaga_scf needs a B200RHF / B200UHF SCF object (no CPU fallback)")  # cf. :187
-    if dm_environment_virtual is not None and np.any(np.asarray(dm_environment_virtual)):
-        raise NotImplementedError("virtual-orbital Huzinaga projector (PAO) is not on the supported path")
     v = np.asarray(embedding_potential, dtype=np.float64)
     g = np.asarray(dm_environment_occupied, dtype=np.float64)
     if v.ndim != g.ndim or v.ndim != (3 if scf_method.unrestricted else 2):
         raise ValueError("embedding_potential / dm_environment_occupied rank does not match the SCF object")
     ctx = scf_method.ctx
     ctx.scf_setup(scf_method.nelec, scf_method.get_ovlp(), scf_method.get_hcore(), v, g, NBD_HUZINAGA)
+    if dm_environment_virtual is not None:  # :133-134 (the PAO virtual projector)
+        gv = np.asarray(dm_environment_virtual, dtype=np.float64)
+        if gv.shape != g.shape:
+            raise ValueError("dm_environment_virtual must have the shape of dm_environment_occupied")
+        ctx.scf_set_virtual_projector(gv)
     c, e, dm, huz, info = ctx.huzinaga_scf(scf_method.max_cycle, scf_method.conv_tol, dm_conv_tol, use_DIIS,
                                            dm0=dm_initial_guess)
     occ = scf_method.get_occ(e, c)
@@ -233,9 +236,13 @@ def huzinaga_scf(scf_method, embedding_potential, dm_environment_occupied, dm_en
 
 
 def get_huzinaga_operator(fock, dm_occ_S, dm_virt_S=None):
-    """-(F gS + (F gS)^T) per spin (rank 3) or -1/2(...) (rank 2): NumPy form for host-side checks."""
+    """-(F gS + (F gS)^T) [- (F gvS + (F gvS)^T - 2 (gvS)^T F gvS)] per spin (rank 3), halved for rank 2
+    (nbed/scf/huzinaga_scf.py:65-90): NumPy form for host-side checks; the loop uses the device kernels."""
     fds = np.einsum("...ij,...jk->...ik", fock, dm_occ_S)
     out = fds + np.swapaxes(fds, -1, -2)
+    if dm_virt_S is not None:
+        fdv = np.einsum("...ij,...jk->...ik", fock, dm_virt_S)
+        out = out + fdv + np.swapaxes(fdv, -1, -2) - 2 * np.einsum("...ij,...jk->...ik", np.swapaxes(dm_virt_S, -1, -2), fdv)
     return out * (-0.5 if fds.ndim == 2 else -1.0)
 
 

@@ -180,3 +180,39 @@ def test_sc_object_protocol_drives_the_reference_style_loop(ctx):
     assert np.abs(rg.get_veff(dm=dm[0] * 2) - rc.get_veff(dm=dm[0] * 2)).max() < 1e-10
     e_g, e_c = gpu.energy_tot(dm=r1[2]), cpu.energy_tot(dm=r0[2])
     assert abs(e_g - e_c) < 1e-9
+
+
+@pytest.mark.parametrize("restricted", [False, True])
+def test_huzinaga_virtual_orbital_projector(ctx, restricted):
+    """dm_environment_virtual (the PAO virtual projector of nbed/driver.py:566-575; second term of
+    get_huzinaga_operator, huzinaga_scf.py:82-88) against the oracle, iterate by iterate."""
+    from nbed_b200 import B200RHF, B200UHF, get_huzinaga_operator, huzinaga_scf
+
+    p, b = _problem("C2_h2o_ccpvdz", 3.0)
+    w, v = np.linalg.eigh(p.ovlp)
+    x = (v / np.sqrt(w)) @ v.T
+    _, c = np.linalg.eigh(x @ p.hcore @ x)
+    cv = (x @ c)[:, -3:]  # three high-lying S-orthonormal orbitals play the environment's virtuals
+    gv = np.array([cv @ cv.T, cv[:, :2] @ cv[:, :2].T])
+    ctx.load_cderi(b)
+    if restricted:
+        args = (p.v_emb[0], 2.0 * p.dm_enviro[0], 2.0 * gv[0])
+        cpu = ps.DFRHF(p.ovlp, p.hcore, b, p.nelec, max_cycle=30, conv_tol=1e-8)
+        gpu = B200RHF(ctx, p.ovlp, p.hcore, p.nelec, max_cycle=30, conv_tol=1e-8)
+    else:
+        args = (p.v_emb, p.dm_enviro, gv)
+        cpu = ps.DFUHF(p.ovlp, p.hcore, b, p.nelec, max_cycle=30, conv_tol=1e-8)
+        gpu = B200UHF(ctx, p.ovlp, p.hcore, p.nelec, max_cycle=30, conv_tol=1e-8)
+    tr = []
+    c0, e0, d0, h0, conv0 = nr.huzinaga_scf(cpu, args[0], args[1], dm_environment_virtual=args[2], trace=tr)
+    c1, e1, d1, h1, conv1, info = huzinaga_scf(gpu, args[0], args[1], dm_environment_virtual=args[2], return_info=True)
+    _same_stop(info, conv0, tr)
+    for k, t in enumerate(tr[: info["cycles"]]):
+        assert np.abs(info["trace"][k, : (1 if restricted else 2)] - np.atleast_1d(t["energy"])).max() < E_TOL, k
+    assert np.abs(np.asarray(d1) - np.asarray(d0)).max() < 1e-8 and np.abs(h1 - h0).max() < 1e-7
+    # the virtual term really contributes, and the host-side formula agrees with the oracle's
+    _, _, _, h_occ_only, _ = huzinaga_scf(gpu, args[0], args[1])
+    assert np.abs(h1 - h_occ_only).max() > 1e-3
+    f = np.random.default_rng(0).normal(size=np.shape(args[1]))
+    gs, gvs = args[1] @ p.ovlp, args[2] @ p.ovlp
+    assert np.abs(get_huzinaga_operator(f, gs, gvs) - nr.get_huzinaga_operator(f, gs, gvs)).max() < 1e-13
