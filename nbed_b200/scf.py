@@ -272,3 +272,22 @@ def mu_embed(localized_scf, embedding_potential, dm_enviro, mu_level_shift: floa
     if return_info:
         return localized_scf, v_emb, info
     return localized_scf, v_emb
+
+
+# ---- nbed/driver.py:540-632 (NbedDriver._huzinaga_embed, without the PAO orbital reshuffling of :604-619) --------
+def huzinaga_embed(active_scf, embedding_potential, dm_enviro, dm_environment_virtual=None, dmat_initial_guess=None):
+    """Runs ``huzinaga_scf`` and writes the result onto the SCF object the way the driver does: patched ``get_hcore``
+    (:595-597), ``mo_occ / mo_coeff / mo_energy`` (:602-622), ``e_tot = energy_tot(dm)`` (:627, one more J/K build on
+    the device) and ``converged``.  Returns ``(active_scf, v_emb)`` with ``v_emb = huzinaga_op + embedding_potential``."""
+    c, e, dm, huz, conv = huzinaga_scf(active_scf, embedding_potential, dm_enviro,
+                                       dm_environment_virtual=dm_environment_virtual, dm_conv_tol=1e-6,
+                                       dm_initial_guess=dmat_initial_guess)
+    hcore_std = active_scf.get_hcore()
+    v_emb = huz + np.asarray(embedding_potential)
+    active_scf.get_hcore = lambda *args: hcore_std + v_emb
+    active_scf.mo_occ = active_scf.get_occ(e, c)
+    active_scf.mo_coeff = c
+    active_scf.mo_energy = e
+    active_scf.e_tot = active_scf.energy_tot(dm=dm)
+    active_scf.converged = conv
+    return active_scf, v_emb

@@ -216,3 +216,19 @@ def test_huzinaga_virtual_orbital_projector(ctx, restricted):
     f = np.random.default_rng(0).normal(size=np.shape(args[1]))
     gs, gvs = args[1] @ p.ovlp, args[2] @ p.ovlp
     assert np.abs(get_huzinaga_operator(f, gs, gvs) - nr.get_huzinaga_operator(f, gs, gvs)).max() < 1e-13
+
+
+def test_huzinaga_embed_driver_wrapper(ctx):
+    """NbedDriver._huzinaga_embed (nbed/driver.py:540-632): SCF + patched core Hamiltonian + e_tot from one more J/K."""
+    from nbed_b200 import B200UHF, huzinaga_embed
+
+    p, b = _problem("C2_h2o_ccpvdz", 3.0)
+    ctx.load_cderi(b)
+    cpu = ps.DFUHF(p.ovlp, p.hcore, b, p.nelec, e_nuc=0.75, max_cycle=30, conv_tol=1e-8)
+    cpu, v0 = nr.huzinaga_embed(cpu, p.v_emb, p.dm_enviro)
+    gpu = B200UHF(ctx, p.ovlp, p.hcore, p.nelec, e_nuc=0.75, max_cycle=30, conv_tol=1e-8)
+    gpu, v1 = huzinaga_embed(gpu, p.v_emb, p.dm_enviro)
+    assert gpu.converged == cpu.converged and abs(gpu.e_tot - cpu.e_tot) < E_TOL
+    assert np.abs(v1 - v0).max() < 1e-7 and np.abs(gpu.get_hcore() - cpu.get_hcore()).max() < 1e-7
+    assert np.array_equal(gpu.mo_occ, cpu.mo_occ) and np.abs(gpu.mo_energy - cpu.mo_energy).max() < 1e-8
+    assert gpu.get_hcore().shape == (2, p.n, p.n)
