@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
         const int i = 8 * ni + 2 * tq + r;
         const bool col_ok = i < ncol;
         double* xo = p.X;
-        if (col_ok) xo += __ldg(p.xbase + col0 + i) + P * __ldg(p.xstride + col0 + i) + gq;
+        if (col_ok) xo += __ldcg(p.xbase + col0 + i) + P * __ldcg(p.xstride + col0 + i) + gq;  // tables change per call
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
           const int I = 8 * s + warp;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(256) j_pass_kernel(const double2* __restrict__
     for (int u = 0; u < 8; ++u) {
 #pragma unroll
       for (int s = 0; s < NSET; ++s) {
-        const double r = __ldg(rho + (long)s * naux + p + u);
+        const double r = __ldcg(rho + (long)s * naux + p + u);
         acc[s].x = fma(r, v[u].x, acc[s].x);
         acc[s].y = fma(r, v[u].y, acc[s].y);
       }
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(256) j_pass_kernel(const double2* __restrict__
     const double2 v = __ldcs(b + (long)p * E2);
 #pragma unroll
     for (int s = 0; s < NSET; ++s) {
-      const double r = __ldg(rho + (long)s * naux + p);
+      const double r = __ldcg(rho + (long)s * naux + p);
       acc[s].x = fma(r, v.x, acc[s].x);
       acc[s].y = fma(r, v.y, acc[s].y);
     }
@@ -484,6 +484,14 @@ __global__ void __launch_bounds__(256) j_pass_kernel(const double2* __restrict__
   for (int s = 0; s < NSET; ++s) part[((long)split * NSET + s) * E2 + idx] = acc[s];
 }
 
+// NOTE on caching (a bug found in round 1): rho changes every SCF cycle, and this kernel co-runs with the K Gram on
+// the same SMs.  Loaded through the non-coherent path (__ldg / ld.global.nc) it occasionally returned the PREVIOUS
+// cycle's values - lines of that cache evidently survive when another grid keeps the SM busy across the launch
+// boundary - which perturbed J by ~1e-6 near convergence and made repeated runs differ.  Everything that is rewritten
+// between launches and read by a kernel that may share an SM with another grid is therefore loaded with
+// ld.global.cg (L2 only): rho here, the partial sums in j_finalize_kernel, the layout tables in the panel kernel.
+// tools/determinism.py checks that repeated SCF runs are bit-identical in every mode.
+//
 // TMA-fed variant of pass 2: persistent CTAs (a few per SM), a producer warp streams tile k of the aux rows of one
 // P-range through a ring of 8 KiB bulk copies, four consumer warps accumulate rho[P] * tile in registers.  It keeps
 // ~64 KiB in flight per CTA with 160 threads and 17 registers' worth of accumulators, so it reaches HBM speed next
@@ -564,7 +572,7 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
     for (int p = p0; p < p1; ++p) {
       double r[NSET];
 #pragma unroll
-      for (int s = 0; s < NSET; ++s) r[s] = __ldg(rho + (long)s * naux + p);
+      for (int s = 0; s < NSET; ++s) r[s] = __ldcg(rho + (long)s * naux + p);
       if (p > p0) mbar_wait_a(full_a + 8u * st, ph);
       const double2* t2 = reinterpret_cast<const double2*>(stages + (size_t)st * TILE_ELEMS);
       double2 v[JP_Q];
@@ -605,7 +613,7 @@ __global__ void j_finalize_kernel(const double* __restrict__ part, const int* __
   const long off = (long)inv[I * nb + Jt] * TILE_ELEMS + tile_swz(hi & 31, lo & 31);
   for (int s = 0; s < nset; ++s) {
     double v = 0.0;
-    for (int sp = 0; sp < nsplit; ++sp) v += part[((long)sp * nset + s) * E + off];
+    for (int sp = 0; sp < nsplit; ++sp) v += __ldcg(part + ((long)sp * nset + s) * E + off);  // (L2: see j_pass note)
     J[((long)s * n + mu) * n + nu] = v;
   }
 }

@@ -184,6 +184,11 @@ struct DiisState {
   }
 };
 
+struct PlanDev {
+  DBuf<uint32_t> events;
+  DBuf<int> begin;
+};
+
 struct nbd_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -195,6 +200,7 @@ struct nbd_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
   int overlap = 1;
+  int eig_threads = 1;  // second spin's full eigensolve issued from a helper thread on the side stream
   int dist_eig = 1;
   int gemm_tile = 0;      // tuning: force the GEMM tile size (0 = heuristic)
   int jpass_variant = 0;  // 0: TMA-fed persistent pass 2, 1: LDG streaming pass 2
@@ -223,9 +229,7 @@ struct nbd_ctx {
   // ---- J/K workspaces ----
   DBuf<double> d_orb, d_wt, d_X, d_rho, d_jpart, d_jk;  // d_jk = [J sets | K sets] contiguous (all-reduce buffer)
   DBuf<int> d_setbegin;
-  PanelPlan plan;
-  DBuf<uint32_t> d_events;
-  DBuf<int> d_evbegin;
+  std::map<int, PlanDev> plans;  // device copies of the panel kernel's task lists, keyed by ring depth
   DBuf<unsigned int> d_jcounter;
   DBuf<long> d_xtab;  // group-major layout tables of the half-transformed tensor: [xbase | xstride]
 
@@ -358,43 +362,38 @@ static XLayout make_xlayout(nbd_ctx* c, int np, int Ntot, const std::vector<std:
 }
 
 // X (group-major, tables in c->d_xtab) for aux rows [p0, p0+np) and all Ntot orbital rows of d_orb ([Ntot][n_ld]).
-static void half_transform(nbd_ctx* c, int p0, int np, const double* d_orb, int Ntot, double* d_X) {
-  const long* xbase = c->d_xtab.p;
-  const long* xstride = c->d_xtab.p + Ntot;
-  if (c->jk_variant == 1) {
-    dim3 g(c->nb, np);
-    symm_panel_simple_kernel<<<g, 256, 0, c->stream>>>(c->Bt + (long)p0 * c->ntiles * TILE_ELEMS, c->d_inv.p, d_orb,
-                                                        d_X, xbase, xstride, c->ntiles, c->nb, c->n_ld, Ntot);
-    LAUNCH_CHECK(c);
-    return;
-  }
+// One launch of the panel kernel on the orbital columns [col_begin, col_begin + ncols) of d_orb.
+static void half_transform_cols(nbd_ctx* c, int p0, int np, const double* d_orb, int Ntot, int col_begin, int ncols,
+                                double* d_X, int nb_force) {
+  const long* xbase = c->d_xtab.p + col_begin;
+  const long* xstride = c->d_xtab.p + Ntot + col_begin;
   const int nslot = (c->nb + 7) / 8;
-  NBD_REQUIRE(nslot <= 12, NBD_ERR_UNSUPPORTED, "nao = %d exceeds the 3072-AO envelope of the panel kernel", c->nao);
   auto smem_for = [&](int ncolmax, int stages) {
     const size_t ct = (((size_t)(ncolmax + 1) * (c->n_ld + 4) * 8) + 127) & ~(size_t)127;
     return (size_t)512 + ct + (size_t)stages * TILE_BYTES;
   };
-  int NBsel = (Ntot > 8 && nslot <= 6) ? 2 : 1;
-  if (NBsel == 2 && smem_for(std::min(16, Ntot), 6) > c->smem_optin) NBsel = 1;
-  const int ncolmax = std::min(8 * NBsel, Ntot);
+  int NBsel = nb_force ? nb_force : ((ncols > 8 && nslot <= 6) ? 2 : 1);
+  if (NBsel == 2 && smem_for(std::min(16, ncols), 6) > c->smem_optin) NBsel = 1;
+  const int ncolmax = std::min(8 * NBsel, ncols);
   NBD_REQUIRE(smem_for(ncolmax, 2) <= c->smem_optin, NBD_ERR_UNSUPPORTED, "nao = %d: orbital slice does not fit shared memory", c->nao);
   int stages = c->panel_stages > 0 ? std::min(16, std::max(2, c->panel_stages)) : 16;
   while (stages > 2 && smem_for(ncolmax, stages) > c->smem_optin) --stages;
-  if (c->plan.nb != c->nb || c->plan.S != stages) {  // per-warp task lists for this (matrix size, ring depth)
-    c->plan = build_panel_plan(c->nb, stages, c->seq);
-    NBD_REQUIRE(c->plan.S == stages, NBD_ERR_STATE, "panel task lists failed their self-check (nb = %d, stages = %d)", c->nb, stages);
-    uint32_t* de = c->d_events.ensure(std::max<size_t>(1, c->plan.events.size()));
-    int* db = c->d_evbegin.ensure(17);
-    NBD_CUDA(cudaMemcpyAsync(de, c->plan.events.data(), sizeof(uint32_t) * c->plan.events.size(), cudaMemcpyHostToDevice, c->stream));
-    NBD_CUDA(cudaMemcpyAsync(db, c->plan.begin.data(), sizeof(int) * 17, cudaMemcpyHostToDevice, c->stream));
+  PlanDev& pd = c->plans[stages];  // per-warp task lists for this (matrix size, ring depth); cleared on re-allocation
+  if (pd.events.p == nullptr) {
+    const PanelPlan plan = build_panel_plan(c->nb, stages, c->seq);
+    NBD_REQUIRE(plan.S == stages, NBD_ERR_STATE, "panel task lists failed their self-check (nb = %d, stages = %d)", c->nb, stages);
+    uint32_t* de = pd.events.ensure(std::max<size_t>(1, plan.events.size()));
+    int* db = pd.begin.ensure(17);
+    NBD_CUDA(cudaMemcpyAsync(de, plan.events.data(), sizeof(uint32_t) * plan.events.size(), cudaMemcpyHostToDevice, c->stream));
+    NBD_CUDA(cudaMemcpyAsync(db, plan.begin.data(), sizeof(int) * 17, cudaMemcpyHostToDevice, c->stream));
     NBD_CUDA(cudaStreamSynchronize(c->stream));
   }
   XArgs a{};
-  a.events = c->d_events.p;
-  a.evbegin = c->d_evbegin.p;
+  a.events = pd.events.p;
+  a.evbegin = pd.begin.p;
   a.Bt = c->Bt + (long)p0 * c->ntiles * TILE_ELEMS;
   a.seq = c->d_seq.p;
-  a.Ct = d_orb;
+  a.Ct = d_orb + (long)col_begin * c->n_ld;
   a.X = d_X;
   a.xbase = xbase;
   a.xstride = xstride;
@@ -402,8 +401,8 @@ static void half_transform(nbd_ctx* c, int p0, int np, const double* d_orb, int 
   a.ntiles = c->ntiles;
   a.nb = c->nb;
   a.n_ld = c->n_ld;
-  a.Ntot = Ntot;
-  a.nslices = (Ntot + 8 * NBsel - 1) / (8 * NBsel);
+  a.Ntot = ncols;
+  a.nslices = (ncols + 8 * NBsel - 1) / (8 * NBsel);
   a.nstages = stages;
   a.ncolmax = ncolmax;
   const long nitems = (long)np * a.nslices;
@@ -426,6 +425,28 @@ static void half_transform(nbd_ctx* c, int p0, int np, const double* d_orb, int 
     else NBD_XK(12, 1);
   }
 #undef NBD_XK
+}
+
+// X (group-major, tables in c->d_xtab) for aux rows [p0, p0+np) and all Ntot orbital rows of d_orb ([Ntot][n_ld]).
+static void half_transform(nbd_ctx* c, int p0, int np, const double* d_orb, int Ntot, double* d_X) {
+  if (c->jk_variant == 1) {
+    dim3 g(c->nb, np);
+    symm_panel_simple_kernel<<<g, 256, 0, c->stream>>>(c->Bt + (long)p0 * c->ntiles * TILE_ELEMS, c->d_inv.p, d_orb,
+                                                        d_X, c->d_xtab.p, c->d_xtab.p + Ntot, c->ntiles, c->nb, c->n_ld, Ntot);
+    LAUNCH_CHECK(c);
+    return;
+  }
+  const int nslot = (c->nb + 7) / 8;
+  NBD_REQUIRE(nslot <= 12, NBD_ERR_UNSUPPORTED, "nao = %d exceeds the 3072-AO envelope of the panel kernel", c->nao);
+  // 16-column slices are DMMA-bound on padded work, 8-column slices HBM-bound: a trailing remainder of <= 8 columns
+  // behind at least one full 16-column slice goes out as its own 8-column launch (40 columns cost 40, not 48)
+  const int rem = Ntot % 16;
+  if (nslot <= 6 && Ntot > 16 && rem > 0 && rem <= 8) {
+    half_transform_cols(c, p0, np, d_orb, Ntot, 0, Ntot - rem, d_X, 2);
+    half_transform_cols(c, p0, np, d_orb, Ntot, Ntot - rem, rem, d_X, 1);
+    return;
+  }
+  half_transform_cols(c, p0, np, d_orb, Ntot, 0, Ntot, d_X, 0);
 }
 
 // d_orb [Ntot][n_ld] (scaled orbitals), d_wt [Ntot][n_ld] (= sign * orbitals).
@@ -610,7 +631,7 @@ static void eigh_batched(nbd_ctx* c, double* A, double* w, int n, int batch) {
   // single rank, two spins: the second solve is issued from a helper thread on the side stream.  dsyevd blocks its
   // calling thread on internal synchronisations, so only two issuing threads let the two solves overlap
   // (35.2 -> 30.8 ms at n = 1376, profiles/eig_bench_r01.log)
-  const bool two_threads = !dist && batch == 2 && c->overlap && n >= 512;
+  const bool two_threads = !dist && batch == 2 && c->overlap && c->eig_threads && n >= 512;
   {
     StageScope ts(c->timers, c->stream, "eigh");
     std::future<cusolverStatus_t> side;
@@ -820,6 +841,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "x_budget_mb") c->x_budget_bytes = value << 20;
   else if (k == "timers") c->timers.enabled = value != 0;
   else if (k == "overlap") c->overlap = (int)value;
+  else if (k == "eig_threads") c->eig_threads = (int)value;
   else if (k == "dist_eig") c->dist_eig = (int)value;
   else if (k == "panel_stages") c->panel_stages = (int)value;
   else if (k == "jpass_variant") c->jpass_variant = (int)value;
@@ -895,7 +917,7 @@ int nbd_cderi_alloc(nbd_ctx* c, int nao, int naux_local) {
     c->npair = (long)nao * (nao + 1) / 2;
     c->naux = naux_local;
     c->seq = build_tile_sequence(c->nb);
-    c->plan = PanelPlan();
+    c->plans.clear();
     NBD_REQUIRE((int)c->seq.size() == c->ntiles, NBD_ERR_STATE, "tile sequence has %zu entries, expected %d", c->seq.size(), c->ntiles);
     c->inv.assign((size_t)c->nb * c->nb, -1);
     for (int k = 0; k < c->ntiles; ++k) c->inv[(size_t)(c->seq[k] >> 16) * c->nb + (c->seq[k] & 0xffff)] = k;

@@ -127,3 +127,25 @@ def test_open_shell_and_restricted_mu_path(ctx):
     with pytest.raises(NbdError) as ei:
         ctx.mu_scf(10, 1e-8, 0.0, 2.0 * p.dm_enviro[0])
     assert ei.value.code == -4
+
+
+def test_repeated_runs_are_bit_identical(ctx):
+    """Regression test for a stale-cache bug found in round 1 (rho read through the non-coherent path while pass 2
+    co-runs with the K Gram): the same SCF, run three times, must give bit-identical iterates in every mode."""
+    cfg = dict(syn.CONFIGS["C4_h2o32_def2tzvp"], naux=64)
+    p = syn.make_problem(seed=3, scale=6.0 / np.sqrt(cfg["n"] * cfg["naux"]), **cfg)
+    ctx.cderi_alloc(p.n, p.naux)
+    ctx.cderi_synth(p.seed, p.scale, 0)
+    for mode in (1, 0):
+        ctx.set_option("eig_mode", mode)
+        try:
+            runs = []
+            for _ in range(3):
+                ctx.scf_setup(p.nelec, p.ovlp, p.hcore, p.v_emb, p.dm_enviro, NBD_HUZINAGA)
+                c, e, d, h, info = ctx.huzinaga_scf(25, 1e-9, 1e-7, True)
+                runs.append((info["trace"].copy(), d.copy()))
+        finally:
+            ctx.set_option("eig_mode", 1)
+        for tr, d in runs[1:]:
+            assert tr.shape == runs[0][0].shape and np.array_equal(tr, runs[0][0]), mode
+            assert np.array_equal(d, runs[0][1]), mode
