@@ -31,7 +31,9 @@ constexpr int GEMM_BK = 16;
 constexpr int GEMM_STAGES = 3;
 
 // A_MC: A tile stored [k][m] (m contiguous in global memory), else [m][k].  B_NC: B tile stored [k][n].
-template <int BM, int BN, int WM, int WN, bool A_MC, bool B_NC>
+// VEC (only with A_MC && B_NC): operands are 16-byte aligned with even extents, tiles are staged with 16-byte
+// cp.async.cg (L2 only - the K Gram co-runs with pass 2, see the caching note in jk.cuh - and half the copy count).
+template <int BM, int BN, int WM, int WN, bool A_MC, bool B_NC, bool VEC = false>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 gemm_dmma_kernel(GemmArgs g) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
@@ -92,6 +94,23 @@ gemm_dmma_kernel(GemmArgs g) {
     const int k0 = kt * BK;
     double* as = As + st * A_ELEMS;
     double* bs = Bs + st * B_ELEMS;
+    if (VEC) {
+      // pairs along the contiguous index: e = tid + j NT ; m = 2 (e % (BM/2)) , k = e / (BM/2)
+      constexpr int AV = BM * BK / 2 / NT, BV = BN * BK / 2 / NT;
+#pragma unroll
+      for (int j = 0; j < AV; ++j) {
+        const int e = tid + j * NT, m = 2 * (e % (BM / 2)), k = e / (BM / 2);
+        const bool ok = (m0 + m < g.M) && (k0 + k < g.K);  // M even: a pair never straddles the edge
+        cp_async16(as + k * A_LD + m, ok ? A + (long)(m0 + m) + (long)(k0 + k) * g.a_ks : A, ok);
+      }
+#pragma unroll
+      for (int j = 0; j < BV; ++j) {
+        const int e = tid + j * NT, n = 2 * (e % (BN / 2)), k = e / (BN / 2);
+        const bool ok = (n0 + n < g.N) && (k0 + k < g.K);
+        cp_async16(bs + k * B_LD + n, ok ? B + (long)(n0 + n) + (long)(k0 + k) * g.b_ks : B, ok);
+      }
+      return;
+    }
     const double* ap = a_src + (long)k0 * g.a_ks;
     const double* bp = b_src + (long)k0 * g.b_ks;
 #pragma unroll
@@ -191,7 +210,7 @@ __global__ void gemm_simple_kernel(GemmArgs g, int tile) {
   *p = v;
 }
 
-template <int BM, int BN, int WM, int WN, bool A_MC, bool B_NC>
+template <int BM, int BN, int WM, int WN, bool A_MC, bool B_NC, bool VEC = false>
 inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g) {
   constexpr int BK = GEMM_BK;
   constexpr int A_LD = A_MC ? (BM + 4) : (BK + 4);
@@ -200,7 +219,7 @@ inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g) {
   constexpr int B_ELEMS = B_NC ? BK * B_LD : BN * B_LD;
   constexpr int SMEM = GEMM_STAGES * (A_ELEMS + B_ELEMS) * 8;
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
-  auto kern = gemm_dmma_kernel<BM, BN, WM, WN, A_MC, B_NC>;
+  auto kern = gemm_dmma_kernel<BM, BN, WM, WN, A_MC, B_NC, VEC>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -240,8 +259,14 @@ inline cudaError_t launch_gemm(cudaStream_t st, GemmArgs g, int variant, long* l
   const bool b_nc = (g.b_js == 1);
   // lower_only masks whole tiles above the diagonal; every element with col <= row is still produced for
   // any tile size, which is all the mirror kernel needs.
+  // 16-byte staging is possible when both operands are contiguous along the tile's leading index, 16-byte aligned,
+  // with even extents and even strides everywhere
+  auto even = [](long x) { return (x & 1) == 0; };
+  const bool vec = a_mc && b_nc && even(g.M) && even(g.N) && even(g.a_ks) && even(g.b_ks) && even(g.strideA) &&
+                   even(g.strideB) && ((reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.B)) & 15) == 0;
 #define NBD_GEMM_DISPATCH(BM, BN, WM, WN)                                          \
   do {                                                                             \
+    if (vec) return launch_gemm_cfg<BM, BN, WM, WN, true, true, true>(st, g);      \
     if (a_mc && b_nc) return launch_gemm_cfg<BM, BN, WM, WN, true, true>(st, g);   \
     if (a_mc && !b_nc) return launch_gemm_cfg<BM, BN, WM, WN, true, false>(st, g); \
     if (!a_mc && b_nc) return launch_gemm_cfg<BM, BN, WM, WN, false, true>(st, g); \
