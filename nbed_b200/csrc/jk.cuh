@@ -610,7 +610,7 @@ __global__ void j_finalize_kernel(const double* __restrict__ part, const int* __
   if (nu >= n) return;
   const int hi = max(mu, nu), lo = min(mu, nu);
   const int I = hi >> 5, Jt = lo >> 5;
-  const long off = (long)inv[I * nb + Jt] * TILE_ELEMS + tile_swz(hi & 31, lo & 31);
+  const long off = (long)__ldcg(inv + I * nb + Jt) * TILE_ELEMS + tile_swz(hi & 31, lo & 31);  // (table changes per tensor)
   for (int s = 0; s < nset; ++s) {
     double v = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) v += __ldcg(part + ((long)sp * nset + s) * E + off);  // (L2: see j_pass note)
