@@ -216,6 +216,9 @@ def run_b200(args):
     cfg, p = build_problem(key)
     n, naux = cfg["n"], cfg["naux"]
     ctx = B200Context(local)
+    for kv in args.option:  # tuning experiments (A/B of a kernel variant); the default line sets none
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     if world > 1:
         ctx.comm_init_from_torch()
     # contiguous aux shard of this rank
@@ -330,7 +333,8 @@ def run_b200(args):
         "config": {"workload": desc, "n": n, "naux": naux, "nocc_per_spin": cfg["nocc"], "n_env": cfg["n_env"],
                    "sharding": f"aux-index x{world}", "l2": "3-centre tensor (>= 4 GB per rank) exceeds the 126 MB L2: "
                    "every iteration streams it from HBM", "eigensolver": "included in value; reported separately under "
-                   "stages_ms.eigh (cuSOLVER dsyevd) and stages_ms.eig_sub (filtered subspace iteration)"},
+                   "stages_ms.eigh (cuSOLVER dsyevd) and stages_ms.eig_sub (filtered subspace iteration)",
+                   **({"options": args.option} if args.option else {})},
         "wall_ms_per_step": wall_ms / args.steps,
         "stages_ms": stages,
         "iters_per_s_excl_eigh": 1e3 / max(1e-9, stages["iter_total"] - stages["eigh"] - stages["eig_sub"]),
@@ -428,6 +432,7 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=48)
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / ao2mo / cpu_baseline (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=INT", help="nbd_set_option before the run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

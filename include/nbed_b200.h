@@ -45,7 +45,8 @@ int nbd_set_option(nbd_ctx* ctx, const char* key, long value);
  * Cumulative counters since context creation: "count:sub_applies", "count:sub_outer", "count:sub_fallbacks".
  * Options of nbd_set_option: "jk_variant", "gemm_variant" (1 = simple reference kernels), "jpass_variant"
  * (0 = TMA-fed, 1 = LDG streaming), "eig_mode" (0 = cuSOLVER every cycle, 1 = subspace tracking), "sub_min_nao",
- * "overlap", "dist_eig", "panel_stages", "x_budget_mb", "timers". */
+ * "overlap", "dist_eig", "panel_stages", "panel_hybrid" (1 = 9-10 column slices run 8 columns on DMMA + 1-2 on the
+ * FMA pipe, 0 = padded to 16 DMMA columns), "x_budget_mb", "timers". */
 double nbd_timer_ms(nbd_ctx* ctx, const char* key);
 /* Number of kernels launched by this library since the context was created (bench "gpu_launches"). */
 long nbd_launch_count(nbd_ctx* ctx);

@@ -203,16 +203,24 @@ constexpr int XK_THREADS = (XK_CONSUMER_WARPS + 4) * 32;
 constexpr int XK_CONSUMER_REGS = 240;
 constexpr int XK_PRODUCER_REGS = 24;
 
-template <int NB>
-__device__ __forceinline__ void xk_task_row(double (&acc)[4][NB][2], const double* __restrict__ tile,
-                                            const double* const (&crow)[NB], int colbase, int gq, int tq,
+// NF extra columns (beyond the 8 * NB DMMA columns) ride along on the FP64 FMA pipe: the lane that holds the DMMA
+// A-fragment element (row 8 mi + gq, contraction index 4 ks + tq) multiplies it with the orbital value of the same
+// contraction index, so accf[mi][f] is this lane's partial sum over the contraction indices == tq (mod 4); the four
+// tq lanes are summed once per aux row.  DFMA and DMMA share one pipe at the same FLOP rate (profiles/microbench_r01.md),
+// so 8 + NF columns cost (8 + NF) / 8 of a DMMA block instead of 2 blocks.
+template <int NB, int NF>
+__device__ __forceinline__ void xk_task_row(double (&acc)[4][NB][2], double (&accf)[4][NF > 0 ? NF : 1],
+                                            const double* __restrict__ tile, const double* const (&crow)[NB],
+                                            const double* __restrict__ cf, int ct_ld, int colbase, int gq, int tq,
                                             const int (&xoff)[4]) {
   // fragments of step ks+1 are loaded before the DMMAs of step ks issue (register double buffering)
-  double a[2][4], b[2][NB];
+  double a[2][4], b[2][NB], f[2][NF > 0 ? NF : 1];
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi) a[0][mi] = tile[(8 * mi + gq) * 32 + xoff[0]];
 #pragma unroll
   for (int ni = 0; ni < NB; ++ni) b[0][ni] = crow[ni][colbase + tq];
+#pragma unroll
+  for (int fi = 0; fi < NF; ++fi) f[0][fi] = cf[fi * ct_ld + colbase + tq];
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
     const int cur = ks & 1, nxt = cur ^ 1;
@@ -222,23 +230,31 @@ __device__ __forceinline__ void xk_task_row(double (&acc)[4][NB][2], const doubl
       for (int mi = 0; mi < 4; ++mi) a[nxt][mi] = tile[(8 * mi + gq) * 32 + co];
 #pragma unroll
       for (int ni = 0; ni < NB; ++ni) b[nxt][ni] = crow[ni][colbase + 4 * (ks + 1) + tq];
+#pragma unroll
+      for (int fi = 0; fi < NF; ++fi) f[nxt][fi] = cf[fi * ct_ld + colbase + 4 * (ks + 1) + tq];
     }
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < 4; ++mi) {
 #pragma unroll
       for (int ni = 0; ni < NB; ++ni) dmma(acc[mi][ni], a[cur][mi], b[cur][ni]);
+#pragma unroll
+      for (int fi = 0; fi < NF; ++fi) accf[mi][fi] = fma(a[cur][mi], f[cur][fi], accf[mi][fi]);
+    }
   }
 }
 
-template <int NB>
-__device__ __forceinline__ void xk_task_col(double (&acc)[4][NB][2], const double* __restrict__ tile,
-                                            const double* const (&crow)[NB], int colbase, int tq,
+template <int NB, int NF>
+__device__ __forceinline__ void xk_task_col(double (&acc)[4][NB][2], double (&accf)[4][NF > 0 ? NF : 1],
+                                            const double* __restrict__ tile, const double* const (&crow)[NB],
+                                            const double* __restrict__ cf, int ct_ld, int colbase, int tq,
                                             const int (&yoff)[4]) {
-  double a[2][4], b[2][NB];
+  double a[2][4], b[2][NB], f[2][NF > 0 ? NF : 1];
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi) a[0][mi] = tile[tq * 32 + yoff[mi]];
 #pragma unroll
   for (int ni = 0; ni < NB; ++ni) b[0][ni] = crow[ni][colbase + tq];
+#pragma unroll
+  for (int fi = 0; fi < NF; ++fi) f[0][fi] = cf[fi * ct_ld + colbase + tq];
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
     const int cur = ks & 1, nxt = cur ^ 1;
@@ -247,19 +263,26 @@ __device__ __forceinline__ void xk_task_col(double (&acc)[4][NB][2], const doubl
       for (int mi = 0; mi < 4; ++mi) a[nxt][mi] = tile[(4 * (ks + 1) + tq) * 32 + yoff[mi]];
 #pragma unroll
       for (int ni = 0; ni < NB; ++ni) b[nxt][ni] = crow[ni][colbase + 4 * (ks + 1) + tq];
+#pragma unroll
+      for (int fi = 0; fi < NF; ++fi) f[nxt][fi] = cf[fi * ct_ld + colbase + 4 * (ks + 1) + tq];
     }
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < 4; ++mi) {
 #pragma unroll
       for (int ni = 0; ni < NB; ++ni) dmma(acc[mi][ni], a[cur][mi], b[cur][ni]);
+#pragma unroll
+      for (int fi = 0; fi < NF; ++fi) accf[mi][fi] = fma(a[cur][mi], f[cur][fi], accf[mi][fi]);
+    }
   }
 }
 
-// NSLOT = ceil(nb / 8) panels owned per consumer warp; NB = 8-column blocks per slice (1 or 2).
-template <int NSLOT, int NB>
+// NSLOT = ceil(nb / 8) panels owned per consumer warp; NB = 8-column DMMA blocks per slice (1 or 2); NF = extra
+// FMA-pipe columns per slice (0-2; the host launches NF > 0 only on exactly 8 * NB + NF columns, one slice).
+template <int NSLOT, int NB, int NF>
 __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
   extern __shared__ __align__(128) unsigned char xsm[];
-  constexpr int NCOL = 8 * NB;
+  constexpr int NCOL = 8 * NB + NF;
+  constexpr int NFA = NF > 0 ? NF : 1;
   const int S = p.nstages;
   uint64_t* full = reinterpret_cast<uint64_t*>(xsm);  // 2S "full" barriers (tile q uses q mod 2S) ...
   uint64_t* empty = full + 32;                        // ... over S data stages / "empty" barriers (q mod S)
@@ -332,14 +355,19 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
   const double* crow[NB];
 #pragma unroll
   for (int ni = 0; ni < NB; ++ni) crow[ni] = cts + (size_t)min(8 * ni + gq, ncol) * ct_ld;
+  const double* cf = cts + (size_t)min(8 * NB, ncol) * ct_ld;  // rows of the NF extra columns
 
   double X[NSLOT][4][NB][2];
+  double Xf[NSLOT][4][NFA];
 #pragma unroll
   for (int s = 0; s < NSLOT; ++s)
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < 4; ++mi) {
 #pragma unroll
       for (int ni = 0; ni < NB; ++ni) X[s][mi][ni][0] = X[s][mi][ni][1] = 0.0;
+#pragma unroll
+      for (int fi = 0; fi < NFA; ++fi) Xf[s][mi][fi] = 0.0;
+    }
 
   const int e0 = __ldg(p.evbegin + warp), e1 = __ldg(p.evbegin + warp + 1);
   if (e0 == e1) return;  // this warp owns no panel of this matrix size: nothing to compute, wait for or write
@@ -362,13 +390,13 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
           const int slot = I >> 3;
 #pragma unroll
           for (int s = 0; s < NSLOT; ++s)
-            if (slot == s) xk_task_row<NB>(X[s], tile, crow, 32 * J, gq, tq, xoff);
+            if (slot == s) xk_task_row<NB, NF>(X[s], Xf[s], tile, crow, cf, ct_ld, 32 * J, gq, tq, xoff);
         }
         if (ev & (2u << 26)) {
           const int slot = J >> 3;
 #pragma unroll
           for (int s = 0; s < NSLOT; ++s)
-            if (slot == s) xk_task_col<NB>(X[s], tile, crow, 32 * I, tq, yoff);
+            if (slot == s) xk_task_col<NB, NF>(X[s], Xf[s], tile, crow, cf, ct_ld, 32 * I, tq, yoff);
         }
         __syncwarp();
       }
@@ -398,6 +426,23 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
           }
         }
       }
+    // extra columns: sum the four tq lanes' partials, lane tq == fi writes column 8 * NB + fi
+#pragma unroll
+    for (int fi = 0; fi < NF; ++fi) {
+      double* xo = p.X + __ldcg(p.xbase + col0 + 8 * NB + fi) + P * __ldcg(p.xstride + col0 + 8 * NB + fi) + gq;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) {
+        const int I = 8 * s + warp;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          double v = Xf[s][mi][fi];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          if (tq == fi && I < p.nb) xo[32 * I + 8 * mi] = v;
+          Xf[s][mi][fi] = 0.0;
+        }
+      }
+    }
   }
 }
 

@@ -64,96 +64,7 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 
-// ------------------------------------------------------------------------------------------------
-// Small host linear algebra for the DIIS equations (<= 9 x 9): restates what pyscf/lib/diis.py asks of
-// scipy.linalg.eigh / numpy.linalg.solve (reference call site nbed/scf/huzinaga_scf.py:164).
-// ------------------------------------------------------------------------------------------------
-static void jacobi_eigh(int n, std::vector<double> a, std::vector<double>& w, std::vector<double>& v) {
-  v.assign((size_t)n * n, 0.0);
-  for (int i = 0; i < n; ++i) v[(size_t)i * n + i] = 1.0;
-  for (int sweep = 0; sweep < 100; ++sweep) {
-    double off = 0.0, diag = 0.0;
-    for (int p = 0; p < n; ++p) {
-      diag += a[(size_t)p * n + p] * a[(size_t)p * n + p];
-      for (int q = p + 1; q < n; ++q) off += a[(size_t)p * n + q] * a[(size_t)p * n + q];
-    }
-    if (off <= 1e-34 * (diag + 2.0 * off) || off < 1e-300) break;  // off-diagonal norm below 1e-17 of the matrix norm
-    for (int p = 0; p < n; ++p)
-      for (int q = p + 1; q < n; ++q) {
-        const double apq = a[(size_t)p * n + q];
-        if (apq == 0.0) continue;
-        const double app = a[(size_t)p * n + p], aqq = a[(size_t)q * n + q];
-        const double theta = (aqq - app) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < n; ++k) {
-          const double akp = a[(size_t)k * n + p], akq = a[(size_t)k * n + q];
-          a[(size_t)k * n + p] = c * akp - s * akq;
-          a[(size_t)k * n + q] = s * akp + c * akq;
-        }
-        for (int k = 0; k < n; ++k) {
-          const double apk = a[(size_t)p * n + k], aqk = a[(size_t)q * n + k];
-          a[(size_t)p * n + k] = c * apk - s * aqk;
-          a[(size_t)q * n + k] = s * apk + c * aqk;
-        }
-        for (int k = 0; k < n; ++k) {
-          const double vkp = v[(size_t)k * n + p], vkq = v[(size_t)k * n + q];
-          v[(size_t)k * n + p] = c * vkp - s * vkq;
-          v[(size_t)k * n + q] = s * vkp + c * vkq;
-        }
-      }
-  }
-  w.resize(n);
-  for (int i = 0; i < n; ++i) w[i] = a[(size_t)i * n + i];
-}
-
-static bool lu_solve(int n, std::vector<double> a, std::vector<double> b, std::vector<double>& x) {
-  for (int k = 0; k < n; ++k) {
-    int piv = k;
-    for (int i = k + 1; i < n; ++i)
-      if (std::fabs(a[(size_t)i * n + k]) > std::fabs(a[(size_t)piv * n + k])) piv = i;
-    if (a[(size_t)piv * n + k] == 0.0) return false;
-    if (piv != k) {
-      for (int j = 0; j < n; ++j) std::swap(a[(size_t)k * n + j], a[(size_t)piv * n + j]);
-      std::swap(b[k], b[piv]);
-    }
-    for (int i = k + 1; i < n; ++i) {
-      const double f = a[(size_t)i * n + k] / a[(size_t)k * n + k];
-      if (f == 0.0) continue;
-      for (int j = k; j < n; ++j) a[(size_t)i * n + j] -= f * a[(size_t)k * n + j];
-      b[i] -= f * b[k];
-    }
-  }
-  x.assign(n, 0.0);
-  for (int i = n - 1; i >= 0; --i) {
-    double s = b[i];
-    for (int j = i + 1; j < n; ++j) s -= a[(size_t)i * n + j] * x[j];
-    x[i] = s / a[(size_t)i * n + i];
-  }
-  return true;
-}
-
-// c = solution of H c = (1,0,...,0) with the pseudo-inverse fallback of pyscf/lib/diis.py:extrapolate
-static std::vector<double> diis_coefficients(const std::vector<double>& Hfull, int ldh, int nd) {
-  const int m = nd + 1;
-  std::vector<double> h((size_t)m * m), g(m, 0.0), w, v, c;
-  for (int i = 0; i < m; ++i)
-    for (int j = 0; j < m; ++j) h[(size_t)i * m + j] = Hfull[(size_t)i * ldh + j];
-  g[0] = 1.0;
-  jacobi_eigh(m, h, w, v);
-  bool singular = false;
-  for (int i = 0; i < m; ++i)
-    if (std::fabs(w[i]) < 1e-14) singular = true;
-  if (!singular && lu_solve(m, h, g, c)) return c;
-  c.assign(m, 0.0);
-  for (int k = 0; k < m; ++k) {
-    if (std::fabs(w[k]) <= 1e-14) continue;
-    double proj = 0.0;
-    for (int i = 0; i < m; ++i) proj += v[(size_t)i * m + k] * g[i];
-    for (int i = 0; i < m; ++i) c[i] += v[(size_t)i * m + k] * proj / w[k];
-  }
-  return c;
-}
+#include "host_linalg.h"
 
 // ------------------------------------------------------------------------------------------------
 // Context
@@ -204,7 +115,8 @@ struct nbd_ctx {
   int dist_eig = 1;
   int gemm_tile = 0;      // tuning: force the GEMM tile size (0 = heuristic)
   int jpass_variant = 0;  // 0: TMA-fed persistent pass 2, 1: LDG streaming pass 2
-  int panel_stages = 0;  // tuning: cap on the ring depth of the panel kernel (0 = as many as fit)  // distribute the two spins' eigensolves over ranks 0 / 1 when a communicator exists
+  int panel_stages = 0;  // tuning: cap on the ring depth of the panel kernel (0 = as many as fit)
+  int panel_hybrid = 1;  // 9-10 trailing orbital columns: 8 on DMMA + 1-2 on the FMA pipe (0 = pad to 16 DMMA columns)
   std::string err;
   long launches = 0;
   StageTimers timers;
@@ -322,9 +234,9 @@ struct KGroup {
   double alpha;  // +1 / -1 (signed eigen-factors of a dense density)
 };
 
-template <int NSLOT, int NB>
+template <int NSLOT, int NB, int NF = 0>
 static void launch_symm_panel(nbd_ctx* c, const XArgs& a, int grid, size_t smem) {
-  auto kern = symm_panel_kernel<NSLOT, NB>;
+  auto kern = symm_panel_kernel<NSLOT, NB, NF>;
   NBD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, XK_THREADS, smem, c->stream>>>(a);
   LAUNCH_CHECK(c);
@@ -364,7 +276,7 @@ static XLayout make_xlayout(nbd_ctx* c, int np, int Ntot, const std::vector<std:
 // X (group-major, tables in c->d_xtab) for aux rows [p0, p0+np) and all Ntot orbital rows of d_orb ([Ntot][n_ld]).
 // One launch of the panel kernel on the orbital columns [col_begin, col_begin + ncols) of d_orb.
 static void half_transform_cols(nbd_ctx* c, int p0, int np, const double* d_orb, int Ntot, int col_begin, int ncols,
-                                double* d_X, int nb_force) {
+                                double* d_X, int nb_force, int nf = 0) {
   const long* xbase = c->d_xtab.p + col_begin;
   const long* xstride = c->d_xtab.p + Ntot + col_begin;
   const int nslot = (c->nb + 7) / 8;
@@ -374,7 +286,8 @@ static void half_transform_cols(nbd_ctx* c, int p0, int np, const double* d_orb,
   };
   int NBsel = nb_force ? nb_force : ((ncols > 8 && nslot <= 6) ? 2 : 1);
   if (NBsel == 2 && smem_for(std::min(16, ncols), 6) > c->smem_optin) NBsel = 1;
-  const int ncolmax = std::min(8 * NBsel, ncols);
+  if (nf > 0) NBD_REQUIRE(NBsel == 1 && ncols == 8 + nf && nf <= 2 && nslot <= 6, NBD_ERR_STATE, "bad hybrid panel launch");
+  const int ncolmax = nf > 0 ? ncols : std::min(8 * NBsel, ncols);
   NBD_REQUIRE(smem_for(ncolmax, 2) <= c->smem_optin, NBD_ERR_UNSUPPORTED, "nao = %d: orbital slice does not fit shared memory", c->nao);
   int stages = c->panel_stages > 0 ? std::min(16, std::max(2, c->panel_stages)) : 16;
   while (stages > 2 && smem_for(ncolmax, stages) > c->smem_optin) --stages;
@@ -402,7 +315,7 @@ static void half_transform_cols(nbd_ctx* c, int p0, int np, const double* d_orb,
   a.nb = c->nb;
   a.n_ld = c->n_ld;
   a.Ntot = ncols;
-  a.nslices = (ncols + 8 * NBsel - 1) / (8 * NBsel);
+  a.nslices = nf > 0 ? 1 : (ncols + 8 * NBsel - 1) / (8 * NBsel);
   a.nstages = stages;
   a.ncolmax = ncolmax;
   const long nitems = (long)np * a.nslices;
@@ -411,7 +324,18 @@ static void half_transform_cols(nbd_ctx* c, int p0, int np, const double* d_orb,
   grid = std::max<long>(a.nslices, grid / a.nslices * a.nslices);
   const size_t smem = smem_for(ncolmax, stages);
 #define NBD_XK(NS, NBB) launch_symm_panel<NS, NBB>(c, a, (int)grid, smem)
-  if (NBsel == 2) {
+#define NBD_XKF(NS, NFF) launch_symm_panel<NS, 1, NFF>(c, a, (int)grid, smem)
+  if (nf == 1) {
+    if (nslot <= 1) NBD_XKF(1, 1);
+    else if (nslot <= 2) NBD_XKF(2, 1);
+    else if (nslot <= 4) NBD_XKF(4, 1);
+    else NBD_XKF(6, 1);
+  } else if (nf == 2) {
+    if (nslot <= 1) NBD_XKF(1, 2);
+    else if (nslot <= 2) NBD_XKF(2, 2);
+    else if (nslot <= 4) NBD_XKF(4, 2);
+    else NBD_XKF(6, 2);
+  } else if (NBsel == 2) {
     if (nslot <= 1) NBD_XK(1, 2);
     else if (nslot <= 2) NBD_XK(2, 2);
     else if (nslot <= 4) NBD_XK(4, 2);
@@ -425,6 +349,7 @@ static void half_transform_cols(nbd_ctx* c, int p0, int np, const double* d_orb,
     else NBD_XK(12, 1);
   }
 #undef NBD_XK
+#undef NBD_XKF
 }
 
 // X (group-major, tables in c->d_xtab) for aux rows [p0, p0+np) and all Ntot orbital rows of d_orb ([Ntot][n_ld]).
@@ -441,6 +366,12 @@ static void half_transform(nbd_ctx* c, int p0, int np, const double* d_orb, int 
   // 16-column slices are DMMA-bound on padded work, 8-column slices HBM-bound: a trailing remainder of <= 8 columns
   // behind at least one full 16-column slice goes out as its own 8-column launch (40 columns cost 40, not 48)
   const int rem = Ntot % 16;
+  // 9 or 10 trailing columns: 8 on the DMMA path + 1-2 on the FMA pipe in the same launch (cost 9-10, not 16)
+  if (c->panel_hybrid && nslot <= 6 && (rem == 9 || rem == 10)) {
+    if (Ntot > rem) half_transform_cols(c, p0, np, d_orb, Ntot, 0, Ntot - rem, d_X, 2);
+    half_transform_cols(c, p0, np, d_orb, Ntot, Ntot - rem, rem, d_X, 1, rem - 8);
+    return;
+  }
   if (nslot <= 6 && Ntot > 16 && rem > 0 && rem <= 8) {
     half_transform_cols(c, p0, np, d_orb, Ntot, 0, Ntot - rem, d_X, 2);
     half_transform_cols(c, p0, np, d_orb, Ntot, Ntot - rem, rem, d_X, 1);
@@ -844,6 +775,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "eig_threads") c->eig_threads = (int)value;
   else if (k == "dist_eig") c->dist_eig = (int)value;
   else if (k == "panel_stages") c->panel_stages = (int)value;
+  else if (k == "panel_hybrid") c->panel_hybrid = (int)value;
   else if (k == "jpass_variant") c->jpass_variant = (int)value;
   else if (k == "gemm_tile") c->gemm_tile = (int)value;
   else if (k == "eig_mode") { c->eig_mode = (int)value; c->sub_valid = false; }

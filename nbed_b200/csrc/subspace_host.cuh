@@ -68,67 +68,6 @@ static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double
   ++c->sub_applies;
 }
 
-// host: orthonormalise + Rayleigh-Ritz.  G = Y^T Y, H = Y^T A Y  ->  M (Y M orthonormal Ritz vectors), theta ascending
-static bool sub_rayleigh_ritz(int kb, const double* G, const double* H, double* M, double* theta) {
-  std::vector<double> d(kb), gs((size_t)kb * kb), hs((size_t)kb * kb), L((size_t)kb * kb, 0.0), Li((size_t)kb * kb, 0.0);
-  for (int i = 0; i < kb; ++i) {
-    if (!(G[(size_t)i * kb + i] > 0.0)) return false;
-    d[i] = 1.0 / std::sqrt(G[(size_t)i * kb + i]);
-  }
-  for (int i = 0; i < kb; ++i)
-    for (int j = 0; j < kb; ++j) {
-      gs[(size_t)i * kb + j] = 0.5 * (G[(size_t)i * kb + j] + G[(size_t)j * kb + i]) * d[i] * d[j];
-      hs[(size_t)i * kb + j] = 0.5 * (H[(size_t)i * kb + j] + H[(size_t)j * kb + i]) * d[i] * d[j];
-    }
-  for (int j = 0; j < kb; ++j) {  // Cholesky gs = L L^T
-    double s = gs[(size_t)j * kb + j];
-    for (int k = 0; k < j; ++k) s -= L[(size_t)j * kb + k] * L[(size_t)j * kb + k];
-    if (!(s > 1e-12)) return false;  // (columns are normalised: a tiny pivot means a numerically dependent block)
-    L[(size_t)j * kb + j] = std::sqrt(s);
-    for (int i = j + 1; i < kb; ++i) {
-      double t = gs[(size_t)i * kb + j];
-      for (int k = 0; k < j; ++k) t -= L[(size_t)i * kb + k] * L[(size_t)j * kb + k];
-      L[(size_t)i * kb + j] = t / L[(size_t)j * kb + j];
-    }
-  }
-  for (int j = 0; j < kb; ++j) {  // Li = L^-1 (lower)
-    Li[(size_t)j * kb + j] = 1.0 / L[(size_t)j * kb + j];
-    for (int i = j + 1; i < kb; ++i) {
-      double t = 0.0;
-      for (int k = j; k < i; ++k) t -= L[(size_t)i * kb + k] * Li[(size_t)k * kb + j];
-      Li[(size_t)i * kb + j] = t / L[(size_t)i * kb + i];
-    }
-  }
-  std::vector<double> t1((size_t)kb * kb, 0.0), ht((size_t)kb * kb, 0.0), w, q;
-  for (int i = 0; i < kb; ++i)  // t1 = Li hs
-    for (int j = 0; j < kb; ++j) {
-      double t = 0.0;
-      for (int k = 0; k <= i; ++k) t += Li[(size_t)i * kb + k] * hs[(size_t)k * kb + j];
-      t1[(size_t)i * kb + j] = t;
-    }
-  for (int i = 0; i < kb; ++i)  // ht = t1 Li^T
-    for (int j = 0; j < kb; ++j) {
-      double t = 0.0;
-      for (int k = 0; k <= j; ++k) t += t1[(size_t)i * kb + k] * Li[(size_t)j * kb + k];
-      ht[(size_t)i * kb + j] = t;
-    }
-  for (int i = 0; i < kb; ++i)
-    for (int j = 0; j < i; ++j) ht[(size_t)i * kb + j] = ht[(size_t)j * kb + i] = 0.5 * (ht[(size_t)i * kb + j] + ht[(size_t)j * kb + i]);
-  jacobi_eigh(kb, ht, w, q);  // columns of q = eigenvectors
-  std::vector<int> order(kb);
-  for (int i = 0; i < kb; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](int a, int b) { return w[a] < w[b]; });
-  for (int c = 0; c < kb; ++c) {
-    theta[c] = w[order[c]];
-    for (int i = 0; i < kb; ++i) {  // M[i][c] = d_i * sum_k Li[k][i] q[k][order c]
-      double t = 0.0;
-      for (int k = i; k < kb; ++k) t += Li[(size_t)k * kb + i] * q[(size_t)k * kb + order[c]];
-      M[(size_t)i * kb + c] = d[i] * t;
-    }
-  }
-  return true;
-}
-
 // Tracks the KB lowest eigenvectors of Fp ([nspin][n][n], Lowdin basis) starting from c->sV.
 // On success c->sV holds the Ritz vectors, c->sub_theta the Ritz values; returns false when it did not converge.
 template <int KB>

@@ -9,7 +9,9 @@ pytestmark = pytest.mark.gpu
 
 SIZES = [(7, 21, (4, 4)), (24, 72, (5, 4)), (33, 50, (3, 0)), (45, 64, (9, 11)), (174, 96, (9, 9)), (100, 40, (17, 20)),
          # more than 8 AO panels: several accumulator slots per consumer warp (NSLOT = 2, 4, 6) and both column widths
-         (300, 24, (5, 5)), (300, 9, (3, 4)), (520, 12, (3, 0)), (1000, 6, (5, 4)), (1376, 6, (5, 5)), (1376, 4, (3, 3))]
+         (300, 24, (5, 5)), (300, 9, (3, 4)), (520, 12, (3, 0)), (1000, 6, (5, 4)), (1376, 6, (5, 5)), (1376, 4, (3, 3)),
+         # 9 / 10 trailing columns: 8 DMMA columns + 1-2 columns on the FMA pipe, alone and behind 16-column slices
+         (100, 40, (13, 12)), (300, 7, (5, 4)), (520, 8, (13, 13)), (1376, 5, (5, 4)), (1376, 3, (13, 13))]
 
 
 def _cderi(n, naux, seed=3):

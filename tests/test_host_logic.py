@@ -109,3 +109,13 @@ def test_panel_task_lists_keep_their_ring_invariants(tmp_path):
     subprocess.run(["nvcc", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", str(exe), src], check=True, timeout=300)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout[-500:]
+
+
+def test_host_linear_algebra_of_the_scf_drivers(tmp_path):
+    """The library's pure-C++ host maths (Jacobi eigensolver, LU, DIIS coefficients incl. the pseudo-inverse branch of
+    pyscf/lib/diis.py, the Rayleigh-Ritz step of the subspace eigensolver) against manufactured solutions."""
+    exe = tmp_path / "linalg_test"
+    src = os.path.join(ROOT, "tests", "cpp", "linalg_test.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(exe), src], check=True, timeout=300)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "fails=0" in out.stdout, out.stdout[-800:]
