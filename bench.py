@@ -260,7 +260,8 @@ def run_b200(args):
     # cuSOLVER diagonalisation) is INSIDE the timed region and charged to its cycles.
     barrier()
     launches0 = ctx.launch_count
-    sub0 = [ctx.timer_ms(k) for k in ("count:sub_applies", "count:sub_outer", "count:sub_fallbacks")]
+    sub_keys = ("count:sub_applies", "count:sub_outer", "count:sub_fallbacks", "count:sub_cold_starts", "count:sub_lanczos")
+    sub0 = [ctx.timer_ms(k) for k in sub_keys]
     t0 = time.perf_counter()
     ddm_trace, guess_ms, n_guess = [], 0.0, 0
     for step in range(args.steps):
@@ -277,7 +278,7 @@ def run_b200(args):
     barrier()
     t1 = time.perf_counter()
     launches = ctx.launch_count - launches0
-    sub1 = [ctx.timer_ms(k) for k in ("count:sub_applies", "count:sub_outer", "count:sub_fallbacks")]
+    sub1 = [ctx.timer_ms(k) for k in sub_keys]
     log(f"timed {args.steps} iterations in {(t1 - t0) * 1e3:.1f} ms")
     clocks = sampler.stop(t0, t1) if sampler else None
     # device time of the K iterations (CUDA events on the library's stream), max over ranks
@@ -344,6 +345,7 @@ def run_b200(args):
                         "matrix_block_products_per_step": (sub1[0] - sub0[0]) / args.steps,
                         "rayleigh_ritz_per_step": (sub1[1] - sub0[1]) / args.steps,
                         "fallbacks_to_cusolver": sub1[2] - sub0[2],
+                        "cold_starts": sub1[3] - sub0[3], "lanczos_bound_runs": sub1[4] - sub0[4],
                         "ms_per_step": stages["eigh"] + stages["eig_sub"]},
         "jk_only_per_s": 1e3 / stages["jk_total"],
         "jk_two_pass_model": jk_model,

@@ -158,3 +158,28 @@ inline bool sub_rayleigh_ritz(int kb, const double* G, const double* H, double* 
   return true;
 }
 
+
+// Extreme Ritz values of a k-step Lanczos run: alpha[0..k) diagonal, beta[1..k) off-diagonal of the tridiagonal
+// matrix, beta[k] the norm of the last residual.  theta_max + beta[k] bounds the spectrum from above (Zhou & Li,
+// "Bounding the spectrum of large Hermitian matrices"); theta_min - beta[k] is the matching estimate from below.
+inline void lanczos_ritz_bounds(int k, const double* alpha, const double* beta, double* low, double* up) {
+  std::vector<double> t((size_t)k * k, 0.0), w, v;
+  for (int i = 0; i < k; ++i) {
+    t[(size_t)i * k + i] = alpha[i];
+    if (i + 1 < k) t[(size_t)i * k + i + 1] = t[(size_t)(i + 1) * k + i] = beta[i + 1];
+  }
+  jacobi_eigh(k, t, w, v);
+  const double lo = *std::min_element(w.begin(), w.end()), hi = *std::max_element(w.begin(), w.end());
+  *low = lo - beta[k];
+  *up = hi + beta[k];
+}
+
+// Degree of the Chebyshev filter on [a, bu] such that the lowest eigenvalue (estimate lmin <= a) is amplified by at
+// most `cap` relative to the interval: keeps the Gram matrix of a filtered block that is still far from the invariant
+// subspace well inside double precision.  Converged blocks (a - lmin << bu - a) always get max_degree.
+inline int chebyshev_degree(double a, double bu, double lmin, double cap, int max_degree) {
+  const double x0 = 1.0 + 2.0 * std::max(0.0, a - lmin) / std::max(1e-300, bu - a);
+  if (x0 <= 1.0 + 1e-14) return max_degree;
+  const double m = std::acosh(cap) / std::acosh(x0);
+  return (int)std::max(2.0, std::min((double)max_degree, std::floor(m)));
+}

@@ -103,6 +103,7 @@ struct XArgs {
   const uint32_t* events;  // per-warp task lists (PanelPlan)
   const int* evbegin;      // [9] offsets of the 8 consumer warps' lists; [9..16] = first tile index of each list
   int naux, ntiles, nb, n_ld, Ntot, nslices, nstages, ncolmax;
+  int zrow;  // 1: a zero row follows the slice (stands in for the padded columns of a ragged last slice)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -290,9 +291,9 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
   const int slice = blockIdx.x % p.nslices;
   const int col0 = slice * NCOL;
   const int ncol = min(NCOL, p.Ntot - col0);
-  // layout: [512 B barriers][(ncolmax + 1) rows of Ct][S stage buffers]   (sizes fixed by the host)
+  // layout: [512 B barriers][(ncolmax + zrow) rows of Ct][S stage buffers]   (sizes fixed by the host)
   double* cts = reinterpret_cast<double*>(xsm + 512);
-  const size_t ct_bytes = ((size_t)(p.ncolmax + 1) * ct_ld * 8 + 127) & ~(size_t)127;
+  const size_t ct_bytes = ((size_t)(p.ncolmax + p.zrow) * ct_ld * 8 + 127) & ~(size_t)127;
   double* stages = reinterpret_cast<double*>(xsm + 512 + ct_bytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(XK_THREADS, 1) symm_panel_kernel(XArgs p) {
 
   // ===== consumers =====
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(XK_CONSUMER_REGS));
-  for (int i = 0; i <= ncol; ++i) {
+  for (int i = 0; i < ncol + p.zrow; ++i) {
     double* dst = cts + (size_t)i * ct_ld;
     if (i < ncol) {
       const double* src = p.Ct + (size_t)(col0 + i) * p.n_ld;

@@ -161,9 +161,14 @@ struct nbd_ctx {
   int sub_min_nao = 256;  // below this the library eigensolver is cheaper than tracking a 16/32-vector block
   bool last_eig_full = true;
   int sub_kb = 0;
-  long sub_applies = 0, sub_fallbacks = 0, sub_outer = 0;
+  long sub_applies = 0, sub_fallbacks = 0, sub_outer = 0, sub_lanczos = 0, sub_cold_starts = 0;
   double sub_theta[2][32];
-  DBuf<double> sV, sY, sZ, sW, sAV, sPart, sG, sGpart, sM, sTheta, sRpart, sBound;
+  DBuf<double> sV, sY, sZ, sW, sAV, sPart, sG, sGpart, sM, sTheta, sRpart, sBound, sFprev, sLz;
+  // spectral bounds of the filter: 0 = Gershgorin every cycle; 1 = Lanczos once, then widened by ||F'_k - F'_{k-1}||_F
+  int sub_bound_mode = 1;
+  int sub_cold = 1;  // 1: the initial guess starts the block from pseudo-random vectors (no library eigensolve)
+  bool sub_bounds_valid = false, sub_is_cold = false;
+  double sub_up[2] = {0, 0}, sub_low[2] = {0, 0}, sub_up_ref[2] = {0, 0}, sub_low_ref[2] = {0, 0};
   DBuf<unsigned int> sTicket;
   // bench state
   bool bench_ready = false;
@@ -280,17 +285,20 @@ static void half_transform_cols(nbd_ctx* c, int p0, int np, const double* d_orb,
   const long* xbase = c->d_xtab.p + col_begin;
   const long* xstride = c->d_xtab.p + Ntot + col_begin;
   const int nslot = (c->nb + 7) / 8;
-  auto smem_for = [&](int ncolmax, int stages) {
-    const size_t ct = (((size_t)(ncolmax + 1) * (c->n_ld + 4) * 8) + 127) & ~(size_t)127;
+  // a ragged last slice reads its padded columns from a zero row behind the slice; exact slices need none
+  auto zrow_for = [&](int nbsel) { return (nf > 0 || ncols % (8 * nbsel) == 0) ? 0 : 1; };
+  auto smem_for = [&](int ncolmax, int stages, int zrow) {
+    const size_t ct = (((size_t)(ncolmax + zrow) * (c->n_ld + 4) * 8) + 127) & ~(size_t)127;
     return (size_t)512 + ct + (size_t)stages * TILE_BYTES;
   };
   int NBsel = nb_force ? nb_force : ((ncols > 8 && nslot <= 6) ? 2 : 1);
-  if (NBsel == 2 && smem_for(std::min(16, ncols), 6) > c->smem_optin) NBsel = 1;
+  if (NBsel == 2 && smem_for(std::min(16, ncols), 6, zrow_for(2)) > c->smem_optin) NBsel = 1;
   if (nf > 0) NBD_REQUIRE(NBsel == 1 && ncols == 8 + nf && nf <= 2 && nslot <= 6, NBD_ERR_STATE, "bad hybrid panel launch");
   const int ncolmax = nf > 0 ? ncols : std::min(8 * NBsel, ncols);
-  NBD_REQUIRE(smem_for(ncolmax, 2) <= c->smem_optin, NBD_ERR_UNSUPPORTED, "nao = %d: orbital slice does not fit shared memory", c->nao);
+  const int zrow = zrow_for(NBsel);
+  NBD_REQUIRE(smem_for(ncolmax, 2, zrow) <= c->smem_optin, NBD_ERR_UNSUPPORTED, "nao = %d: orbital slice does not fit shared memory", c->nao);
   int stages = c->panel_stages > 0 ? std::min(16, std::max(2, c->panel_stages)) : 16;
-  while (stages > 2 && smem_for(ncolmax, stages) > c->smem_optin) --stages;
+  while (stages > 2 && smem_for(ncolmax, stages, zrow) > c->smem_optin) --stages;
   PlanDev& pd = c->plans[stages];  // per-warp task lists for this (matrix size, ring depth); cleared on re-allocation
   if (pd.events.p == nullptr) {
     const PanelPlan plan = build_panel_plan(c->nb, stages, c->seq);
@@ -318,11 +326,12 @@ static void half_transform_cols(nbd_ctx* c, int p0, int np, const double* d_orb,
   a.nslices = nf > 0 ? 1 : (ncols + 8 * NBsel - 1) / (8 * NBsel);
   a.nstages = stages;
   a.ncolmax = ncolmax;
+  a.zrow = zrow;
   const long nitems = (long)np * a.nslices;
   long grid = std::min<long>(nitems, (long)c->sm_count);
   // gridDim.x must be a multiple of nslices so that a CTA keeps the same orbital slice for all its items
   grid = std::max<long>(a.nslices, grid / a.nslices * a.nslices);
-  const size_t smem = smem_for(ncolmax, stages);
+  const size_t smem = smem_for(ncolmax, stages, zrow);
 #define NBD_XK(NS, NBB) launch_symm_panel<NS, NBB>(c, a, (int)grid, smem)
 #define NBD_XKF(NS, NFF) launch_symm_panel<NS, 1, NFF>(c, a, (int)grid, smem)
   if (nf == 1) {
@@ -779,6 +788,8 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "jpass_variant") c->jpass_variant = (int)value;
   else if (k == "gemm_tile") c->gemm_tile = (int)value;
   else if (k == "eig_mode") { c->eig_mode = (int)value; c->sub_valid = false; }
+  else if (k == "sub_bound") { c->sub_bound_mode = (int)value; c->sub_bounds_valid = false; }
+  else if (k == "sub_cold") c->sub_cold = (int)value;
   else if (k == "sub_min_nao") { c->sub_min_nao = (int)value; c->sub_valid = false; }
   else return NBD_ERR_ARG;
   return NBD_OK;
@@ -790,6 +801,8 @@ double nbd_timer_ms(nbd_ctx* c, const char* key) {
   if (!strcmp(key, "count:sub_applies")) return (double)c->sub_applies;
   if (!strcmp(key, "count:sub_outer")) return (double)c->sub_outer;
   if (!strcmp(key, "count:sub_fallbacks")) return (double)c->sub_fallbacks;
+  if (!strcmp(key, "count:sub_lanczos")) return (double)c->sub_lanczos;
+  if (!strcmp(key, "count:sub_cold_starts")) return (double)c->sub_cold_starts;
   auto it = c->timers.ms.find(key);
   return it == c->timers.ms.end() ? 0.0 : it->second;
 }

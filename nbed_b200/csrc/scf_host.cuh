@@ -69,13 +69,18 @@ static void scf_apply_huzinaga(nbd_ctx* c) {
 // F' = X F X ; eigh ; Ct = V X (rows = MOs)       (huzinaga_scf.py:166-169)
 // allow_subspace: between full cuSOLVER solves the occupied block is tracked by filtered subspace iteration
 // (subspace.cuh); c->last_eig_full tells the caller whether Ct / evals hold the complete spectrum.
-static void scf_diagonalise_lowdin(nbd_ctx* c, bool allow_subspace = false) {
+// allow_cold: with no tracked block yet, start one from pseudo-random vectors instead of a library eigensolve.
+static void scf_diagonalise_lowdin(nbd_ctx* c, bool allow_subspace = false, bool allow_cold = false) {
   const int n = c->nao;
   const long nn = (long)n * n;
   {
     StageScope ts(c->timers, c->stream, "orth");
     gemm_nn(c, n, n, n, c->F.p, n, c->Xh.p, n, c->T1.p, n, 1.0, 0.0, c->nspin, nn, 0, nn);
     gemm_nn(c, n, n, n, c->Xh.p, n, c->T1.p, n, c->T2.p, n, 1.0, 0.0, c->nspin, 0, nn, nn);
+  }
+  if (allow_cold && c->sub_cold && !c->sub_valid) {
+    sub_init_cold(c);
+    allow_subspace = c->sub_valid;
   }
   if (allow_subspace && c->sub_valid && sub_block_size(c) == c->sub_kb) {
     if (sub_solve(c, c->T2.p)) {
@@ -249,6 +254,7 @@ extern "C" int nbd_scf_setup(nbd_ctx* c, int nspin, const int* nelec, const doub
     c->bench_ready = false;
     c->have_virt = false;
     c->sub_valid = false;  // a tracked eigenvector block never survives a change of problem
+    c->sub_bounds_valid = false;
     c->last_eig_full = true;
     finish_call(c);
   });
@@ -284,10 +290,12 @@ struct HuzLoop {
 static void huz_initial(nbd_ctx* c, const double* dm0, HuzLoop& L) {
   const int n = c->nao;
   const long nn = (long)n * n;
+  c->sub_valid = false;  // a new SCF never inherits the eigenvector block or the spectral bounds of the last one
+  c->sub_bounds_valid = false;
   if (!dm0) {
     NBD_CUDA(cudaMemcpyAsync(c->F.p, c->heff.p, sizeof(double) * nn * c->nspin, cudaMemcpyDeviceToDevice, c->stream));
     scf_apply_huzinaga(c);
-    scf_diagonalise_lowdin(c);
+    scf_diagonalise_lowdin(c, false, true);
     scf_make_density(c);
     L.Ntot = scf_stage_occupied(c);
     L.groups = scf_occ_groups(c);
@@ -306,7 +314,7 @@ static void huz_iteration(nbd_ctx* c, int iter, bool use_diis, HuzLoop& L, doubl
   scf_build_fock(c, L.Ntot, L.groups);                                // :156-157
   scf_apply_huzinaga(c);                                              // :159-160
   if (use_diis && iter > 1) diis_update(c, c->diis, c->F.p, nullptr);  // :162-164
-  scf_diagonalise_lowdin(c, true);                                    // :166-169
+  scf_diagonalise_lowdin(c, true, true);                              // :166-169
   scf_make_density(c);                                                // :170-174
   double t[8];
   scf_traces(c, c->heff.p, c->vhf.p, c->Huz.p, true, t);              // :182-194
@@ -346,7 +354,8 @@ extern "C" int nbd_huzinaga_scf(nbd_ctx* c, int max_cycle, double conv_tol, doub
     {
     StageScope ts_all(c->timers, c->stream, "scf_total");
     HuzLoop L;
-    c->sub_valid = false;  // every SCF run starts from a full diagonalisation (or the caller's density)
+    c->sub_valid = false;  // every SCF run starts from scratch (cold block / full diagonalisation / the caller's density)
+    c->sub_bounds_valid = false;
     c->last_eig_full = true;
     huz_initial(c, dm0, L);
     c->diis.init(6, c->nspin * nn, false);

@@ -278,4 +278,74 @@ __global__ void sub_scatter_block_kernel(const double* __restrict__ V, double* _
   if (i < n) Crows[(long)b * cstride + (long)c * n + i] = V[(long)b * vstride + (long)i * kb + c];
 }
 
+// ---- spectral bounds: a few Lanczos steps (Zhou & Li), then ||dF||_F updates while the block is tracked ---------
+// One Lanczos step per spin: w = A v - beta vprev, part[b][blk] = {sum_i w_i v_i, sum_i w_i^2} over the block's rows
+// (one warp per row, 8 rows per CTA; the host adds the blocks in order).
+__global__ void __launch_bounds__(256) sub_lanczos_matvec_kernel(const double* __restrict__ Aall, const double* __restrict__ vall,
+                                                                 const double* __restrict__ vprevall, double beta0, double beta1,
+                                                                 double* __restrict__ wall, double* __restrict__ part, int n) {
+  __shared__ double red[8][2];
+  const int b = blockIdx.y;
+  const double* A = Aall + (long)b * n * n;
+  const double* v = vall + (long)b * n;
+  const double beta = b == 0 ? beta0 : beta1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  double s = 0.0;
+  if (i < n)
+    for (int j = lane; j < n; j += 32) s = fma(A[(long)i * n + j], __ldcg(v + j), s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    double wv = 0.0, ww = 0.0;
+    if (i < n) {
+      const double vi = __ldcg(v + i);
+      s -= beta * __ldcg(vprevall + (long)b * n + i);
+      wall[(long)b * n + i] = s;
+      wv = s * vi;
+      ww = s * s;
+    }
+    red[warp][0] = wv;
+    red[warp][1] = ww;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    part[((long)b * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = t;
+  }
+}
+// vnext = (w - alpha v) / beta_next   (per spin scalars)
+__global__ void sub_lanczos_update_kernel(const double* __restrict__ w, const double* __restrict__ v, double* __restrict__ vnext,
+                                          double alpha0, double alpha1, double ib0, double ib1, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= n) return;
+  const long o = (long)b * n + i;
+  vnext[o] = (__ldcg(w + o) - (b == 0 ? alpha0 : alpha1) * __ldcg(v + o)) * (b == 0 ? ib0 : ib1);
+}
+// part[b][blk] = sum over the block's slice of (A - B)^2   (gridDim.x slices per matrix, fixed order)
+__global__ void __launch_bounds__(256) sub_diffnorm_kernel(const double* __restrict__ A, const double* __restrict__ B, long count,
+                                                           double* __restrict__ part) {
+  __shared__ double red[32];
+  const int b = blockIdx.y;
+  const long per = (count + gridDim.x - 1) / gridDim.x;
+  const long e0 = per * blockIdx.x, e1 = e0 + per < count ? e0 + per : count;
+  double s = 0.0;
+  for (long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const double d = __ldcg(A + (long)b * count + e) - __ldcg(B + (long)b * count + e);
+    s = fma(d, d, s);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) part[(long)b * gridDim.x + blockIdx.x] = s;
+}
+// deterministic pseudo-random start block in [-1, 1) (SplitMix64 of the element index)
+__global__ void sub_random_block_kernel(double* __restrict__ V, long count, unsigned long long seed) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  unsigned long long z = seed * 0xD1B54A32D192ED03ull + (unsigned long long)e + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  V[e] = (double)(z >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+}
+
 }  // namespace nbd

@@ -45,6 +45,137 @@ static void sub_init_from_full(nbd_ctx* c, const double* eigrows, const double* 
   c->sub_valid = true;
 }
 
+// k-step Lanczos per spin (batched): up = theta_max + beta_k (+ 2 % of the Ritz spread), low = theta_min - beta_k.
+static void sub_lanczos_bounds(nbd_ctx* c, const double* Fp, double* up, double* low) {
+  const int n = c->nao, ns = c->nspin;
+  const int steps = std::min(10, n);
+  const int nblk = (n + 7) / 8;
+  double* buf = c->sLz.ensure((size_t)3 * ns * n + (size_t)2 * ns * nblk);
+  double *v = buf, *vprev = buf + (size_t)ns * n, *w = buf + (size_t)2 * ns * n, *part = buf + (size_t)3 * ns * n;
+  // deterministic start vector (same hash as the start block), normalised on the host
+  std::vector<double> v0((size_t)ns * n);
+  for (int s = 0; s < ns; ++s) {
+    double nrm = 0.0;
+    for (int i = 0; i < n; ++i) {
+      unsigned long long z = (unsigned long long)(s * n + i) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z = z ^ (z >> 31);
+      const double x = (double)(z >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+      v0[(size_t)s * n + i] = x;
+      nrm += x * x;
+    }
+    nrm = 1.0 / std::sqrt(nrm);
+    for (int i = 0; i < n; ++i) v0[(size_t)s * n + i] *= nrm;
+  }
+  h2d(c, v, v0.data(), v0.size());
+  NBD_CUDA(cudaMemsetAsync(vprev, 0, sizeof(double) * ns * n, c->stream));
+  double alpha[2][16] = {}, beta[2][17] = {};
+  std::vector<double> hp((size_t)2 * ns * nblk);
+  int k = 0;
+  for (int j = 0; j < steps; ++j) {
+    sub_lanczos_matvec_kernel<<<dim3(nblk, ns), 256, 0, c->stream>>>(Fp, v, vprev, beta[0][j], beta[1][j], w, part, n);
+    LAUNCH_CHECK(c);
+    d2h(c, hp.data(), part, hp.size());
+    NBD_CUDA(cudaStreamSynchronize(c->stream));
+    bool breakdown = false;
+    for (int s = 0; s < ns; ++s) {
+      double a = 0.0, ww = 0.0;
+      for (int b = 0; b < nblk; ++b) {
+        a += hp[((size_t)s * nblk + b) * 2];
+        ww += hp[((size_t)s * nblk + b) * 2 + 1];
+      }
+      alpha[s][j] = a;
+      beta[s][j + 1] = std::sqrt(std::max(0.0, ww - a * a));
+      if (!(beta[s][j + 1] > 1e-10 * (std::fabs(a) + 1e-300))) breakdown = true;
+    }
+    k = j + 1;
+    if (breakdown || k == steps) break;
+    sub_lanczos_update_kernel<<<dim3((n + 255) / 256, ns), 256, 0, c->stream>>>(w, v, vprev, alpha[0][j], alpha[1][j], 1.0 / beta[0][j + 1],
+                                                                                 1.0 / beta[1][j + 1], n);
+    LAUNCH_CHECK(c);
+    std::swap(v, vprev);
+  }
+  for (int s = 0; s < ns; ++s) {
+    double lo, hi;
+    lanczos_ritz_bounds(k, alpha[s], beta[s], &lo, &hi);
+    const double spread = (hi - lo) * 0.02;
+    up[s] = hi + spread;
+    low[s] = lo - spread;
+  }
+  ++c->sub_lanczos;
+}
+
+// Interval [low, up] containing the spectrum of Fp (per spin) for the Chebyshev filter.  Mode 1: the bounds of the
+// last matrix widened by the Frobenius norm of the change (rigorous: |lambda(A + E) - lambda(A)| <= ||E||_2 <= ||E||_F),
+// refreshed by a new Lanczos run whenever they have drifted by a quarter of the width.  Mode 0: row-sum bound.
+static void sub_spectral_bounds(nbd_ctx* c, const double* Fp, double* up, double* low) {
+  const int n = c->nao, ns = c->nspin;
+  const long nn = (long)n * n;
+  if (c->sub_bound_mode == 0) {
+    const int nblk = (n + 7) / 8;
+    double* bp = c->sBound.ensure((size_t)2 * nblk);
+    sub_gershgorin_kernel<<<dim3(nblk, ns), 256, 0, c->stream>>>(Fp, n, bp);
+    LAUNCH_CHECK(c);
+    std::vector<double> hb((size_t)ns * nblk);
+    d2h(c, hb.data(), bp, hb.size());
+    NBD_CUDA(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < ns; ++s) {
+      up[s] = 0.0;
+      for (int k = 0; k < nblk; ++k) up[s] = std::max(up[s], hb[(size_t)s * nblk + k]);
+      low[s] = -up[s];
+    }
+    return;
+  }
+  constexpr int NBLK = 64;
+  double* prev = c->sFprev.ensure((size_t)ns * nn);
+  bool refresh = !c->sub_bounds_valid;
+  if (!refresh) {
+    double* bp = c->sBound.ensure((size_t)2 * NBLK);
+    sub_diffnorm_kernel<<<dim3(NBLK, ns), 256, 0, c->stream>>>(Fp, prev, nn, bp);
+    LAUNCH_CHECK(c);
+    std::vector<double> hb((size_t)ns * NBLK);
+    d2h(c, hb.data(), bp, hb.size());
+    NBD_CUDA(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < ns; ++s) {
+      double d2 = 0.0;
+      for (int k = 0; k < NBLK; ++k) d2 += hb[(size_t)s * NBLK + k];
+      const double d = std::sqrt(d2) * (1.0 + 1e-12);
+      up[s] = c->sub_up[s] + d;
+      low[s] = c->sub_low[s] - d;
+      if (!(up[s] - c->sub_up_ref[s] <= 0.25 * (c->sub_up_ref[s] - c->sub_low_ref[s]))) refresh = true;
+    }
+  }
+  if (refresh) {
+    sub_lanczos_bounds(c, Fp, up, low);
+    for (int s = 0; s < ns; ++s) {
+      c->sub_up_ref[s] = up[s];
+      c->sub_low_ref[s] = low[s];
+    }
+  }
+  for (int s = 0; s < ns; ++s) {
+    c->sub_up[s] = up[s];
+    c->sub_low[s] = low[s];
+  }
+  NBD_CUDA(cudaMemcpyAsync(prev, Fp, sizeof(double) * ns * nn, cudaMemcpyDeviceToDevice, c->stream));
+  c->sub_bounds_valid = true;
+}
+
+// Start block of a cold solve: pseudo-random vectors; the first Rayleigh-Ritz step of sub_solve_t orthonormalises them.
+static void sub_init_cold(nbd_ctx* c) {
+  const int kb = sub_block_size(c);
+  c->sub_valid = false;
+  if (!kb || c->sub_bound_mode != 1) return;
+  sub_alloc(c, kb);
+  const long count = (long)c->nspin * c->nao * kb;
+  sub_random_block_kernel<<<grid1(count, 256), 256, 0, c->stream>>>(c->sV.p, count, 20240ull);
+  LAUNCH_CHECK(c);
+  c->sub_kb = kb;
+  c->sub_valid = true;
+  c->sub_is_cold = true;
+  ++c->sub_cold_starts;
+}
+
 template <int KB>
 static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double* Z, double* out, const double* alpha,
                       const double* shift, const double* beta) {
@@ -75,29 +206,26 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
   const int n = c->nao, ns = c->nspin;
   const long blk = (long)n * KB;
   constexpr int NBLK = 64;
-  const int degree = 24, max_outer = 14;
+  const bool cold = c->sub_is_cold;
+  c->sub_is_cold = false;
+  const int max_degree = 24, max_outer = cold ? 24 : 14;
   const double tol = 1e-10;
-  double bound[2] = {0, 0};
-  {
-    const int nblk = (n + 7) / 8;
-    double* bp = c->sBound.ensure((size_t)2 * nblk);
-    sub_gershgorin_kernel<<<dim3(nblk, ns), 256, 0, c->stream>>>(Fp, n, bp);
-    LAUNCH_CHECK(c);
-    std::vector<double> hb((size_t)ns * nblk);
-    d2h(c, hb.data(), bp, hb.size());
-    NBD_CUDA(cudaStreamSynchronize(c->stream));
-    for (int s = 0; s < ns; ++s)
-      for (int k = 0; k < nblk; ++k) bound[s] = std::max(bound[s], hb[(size_t)s * nblk + k]);
-  }
+  double bound[2] = {0, 0}, lowb[2] = {0, 0}, bu_used[2] = {0, 0};
+  sub_spectral_bounds(c, Fp, bound, lowb);
   const double one[2] = {1.0, 1.0}, zero[2] = {0.0, 0.0};
   double* cur = c->sV.p;  // block to Rayleigh-Ritz next
   for (int outer = 0; outer < max_outer; ++outer) {
     if (outer > 0) {
       // scaled Chebyshev filter of degree `degree` damping [a, bound] (Zhou & Saad), per spin
       double e[2], cc[2], sig[2], sig1[2], al[2], be[2];
+      int degree = max_degree;
       for (int s = 0; s < ns; ++s) {
         const double a = c->sub_theta[s][KB - 1], a0 = c->sub_theta[s][0];
-        const double bu = std::max(bound[s], a + 1e-3) * 1.0000001 + 1e-9;
+        const double bu = std::max(bound[s], a + 1e-3) + 1e-7 * std::fabs(bound[s]) + 1e-9;
+        bu_used[s] = bu;
+        // mode 0 has no estimate of the lowest eigenvalue: tracked blocks (theta_0 converged) take the full degree
+        const double lmin = c->sub_bound_mode == 1 ? std::min(lowb[s], a0) : a0;
+        degree = std::min(degree, chebyshev_degree(a, bu, lmin, 1e10, max_degree));
         e[s] = 0.5 * (bu - a);
         cc[s] = 0.5 * (bu + a);
         sig1[s] = e[s] / (a0 - cc[s]);
@@ -134,6 +262,12 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
       if (!sub_rayleigh_ritz(KB, G.data() + (size_t)s * 2 * KB * KB, G.data() + (size_t)s * 2 * KB * KB + KB * KB,
                              M.data() + (size_t)s * KB * KB, th.data() + (size_t)s * KB))
         return false;
+    // a Ritz value above the assumed upper end of the spectrum: the filter interval was wrong, let the library decide
+    for (int s = 0; s < ns; ++s)
+      if (outer > 0 && th[(size_t)s * KB + KB - 1] > bu_used[s]) {
+        c->sub_bounds_valid = false;
+        return false;
+      }
     h2d(c, c->sM.p, M.data(), M.size());
     h2d(c, c->sTheta.p, th.data(), th.size());
     // rotate into a buffer that is not `cur` (cur may alias sV / sY / sZ): use sAV for A V and the free one for V

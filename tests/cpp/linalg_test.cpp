@@ -99,6 +99,58 @@ int main() {
     std::vector<double> G((size_t)kb * kb, 1.0), Hm((size_t)kb * kb, 1.0), M((size_t)kb * kb), th(kb);
     CHECK(!sub_rayleigh_ritz(kb, G.data(), Hm.data(), M.data(), th.data()), "rank-1 block accepted");
   }
+  // Lanczos bounds: 10 steps on a 200 x 200 symmetric matrix with a known spectrum enclose it from both sides
+  {
+    const int n = 200, k = 10;
+    std::vector<double> A((size_t)n * n, 0.0), d(n);
+    for (int i = 0; i < n; ++i) d[i] = -11.0 + 10.5 * i / (n - 1.0);
+    // A = Q diag(d) Q^T with Q a product of Givens rotations (exact spectrum, dense matrix)
+    for (int i = 0; i < n; ++i) A[(size_t)i * n + i] = d[i];
+    for (int sweep = 0; sweep < 3; ++sweep)
+      for (int i = 0; i + 1 < n; ++i) {
+        const int j = (i * 7 + sweep * 13 + 1) % n;
+        if (j == i) continue;
+        const double c = std::cos(0.7 + i), s = std::sin(0.7 + i);
+        for (int r = 0; r < n; ++r) {
+          const double x = A[(size_t)r * n + i], y = A[(size_t)r * n + j];
+          A[(size_t)r * n + i] = c * x - s * y;
+          A[(size_t)r * n + j] = s * x + c * y;
+        }
+        for (int r = 0; r < n; ++r) {
+          const double x = A[(size_t)i * n + r], y = A[(size_t)j * n + r];
+          A[(size_t)i * n + r] = c * x - s * y;
+          A[(size_t)j * n + r] = s * x + c * y;
+        }
+      }
+    std::vector<double> v(n), vp(n, 0.0), w(n);
+    double nrm = 0;
+    for (int i = 0; i < n; ++i) { v[i] = N(rng); nrm += v[i] * v[i]; }
+    for (auto& e : v) e /= std::sqrt(nrm);
+    double alpha[16] = {}, beta[17] = {};
+    for (int j = 0; j < k; ++j) {
+      double a = 0, ww = 0;
+      for (int i = 0; i < n; ++i) {
+        double t = 0;
+        for (int c = 0; c < n; ++c) t += A[(size_t)i * n + c] * v[c];
+        w[i] = t - beta[j] * vp[i];
+        a += w[i] * v[i];
+        ww += w[i] * w[i];
+      }
+      alpha[j] = a;
+      beta[j + 1] = std::sqrt(std::max(0.0, ww - a * a));
+      for (int i = 0; i < n; ++i) { vp[i] = v[i]; v[i] = (w[i] - a * vp[i]) / beta[j + 1]; }
+    }
+    double lo, up;
+    lanczos_ritz_bounds(k, alpha, beta, &lo, &up);
+    CHECK(up >= -0.5 && up < 4.0 && lo <= -11.0 && lo > -16.0, "lanczos bounds [%.3f, %.3f] for a spectrum [-11, -0.5]", lo, up);
+  }
+  // filter degree: full degree for a converged block, reduced while the block is far from the invariant subspace
+  {
+    CHECK(chebyshev_degree(-10.8, 2.0, -11.2, 1e10, 24) == 24, "tracked block should use the full degree");
+    const int m = chebyshev_degree(-4.8, 2.0, -13.8, 1e10, 24);
+    CHECK(m >= 8 && m <= 16, "cold block degree %d", m);
+    CHECK(chebyshev_degree(0.0, 1.0, -1e6, 1e10, 24) == 2, "degree floor");
+  }
   printf("linalg_test fails=%d\n", fails);
   return fails != 0;
 }

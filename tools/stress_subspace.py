@@ -27,4 +27,5 @@ for case in range(ncase):
         worst_e, worst_d = max(worst_e, de), max(worst_d, dd)
     print(f"case {case}: n={n} naux={naux} nocc={nocc} env={n_env} scale={scale:.2f} diis={diis} cyc {info['cycles']}/{len(tr)} conv {conv0} applies {used:.0f} fallbacks {fell:.0f} dE {de:.1e} dD {dd:.1e} deps {dspec:.1e} {'OK' if ok else 'BAD'}", flush=True)
     bad += 0 if ok else 1
-print(f"STRESS_SUB cases={ncase} bad={bad} worst_dE={worst_e:.2e} worst_dD={worst_d:.2e}")
+print(f"STRESS_SUB cases={ncase} bad={bad} worst_dE={worst_e:.2e} worst_dD={worst_d:.2e} cold_starts={ctx.timer_ms('count:sub_cold_starts'):.0f} "
+      f"lanczos={ctx.timer_ms('count:sub_lanczos'):.0f} outer={ctx.timer_ms('count:sub_outer'):.0f} fallbacks={ctx.timer_ms('count:sub_fallbacks'):.0f}")
