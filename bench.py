@@ -314,8 +314,9 @@ def run_b200(args):
     else:
         roof = {"bound": "tensor", "achieved": ach_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": frac_tensor}
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of this
-    # very configuration (profiles/ncu_r01_raw_key_metrics.csv, capture r01c); other shapes / shard sizes were not captured
-    traffic = 32.000677e9 + 0.444601e9 if (dom == "jk_x" and args.workload == "C4" and world == 1) else None
+    # very configuration (profiles/ncu_r01_raw_key_metrics.csv, capture r01e: symm_panel_kernel<6, 1, 2>, 8 DMMA + 2 FMA
+    # columns); other shapes / shard sizes were not captured
+    traffic = 31.991025e9 + 0.401689e9 if (dom == "jk_x" and args.workload == "C4" and world == 1 and not args.option) else None
     roof.update({"kernel": {"jk_x": "symm_panel_kernel", "jk_j": "j_pass_tma_kernel", "jk_k": "gemm_dmma_kernel (K Gram)"}[dom],
                  "traffic": traffic, "algorithmic_bytes": kern[dom]["bytes"], "algorithmic_flops": kern[dom]["flops"],
                  "ms_per_launch": stages[dom], "peak_source": peak_src,

@@ -42,10 +42,13 @@ int nbd_set_option(nbd_ctx* ctx, const char* key, long value);
  * keys: "jk_x" (pass 1), "jk_rho", "jk_j" (pass 2), "jk_k" (Gram), "jk_total", "allreduce", "fock", "diis", "orth",
  *       "eigh" (cuSOLVER), "eig_sub" (filtered subspace iteration), "eig_bcast", "density", "energy", "iter_total",
  *       "scf_total", "ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm", "ao2mo_total", "spinorb", "build_total".
- * Cumulative counters since context creation: "count:sub_applies", "count:sub_outer", "count:sub_fallbacks".
+ * Cumulative counters since context creation: "count:sub_applies", "count:sub_outer", "count:sub_fallbacks",
+ * "count:sub_cold_starts", "count:sub_lanczos".
  * Options of nbd_set_option: "jk_variant", "gemm_variant" (1 = simple reference kernels), "jpass_variant"
  * (0 = TMA-fed, 1 = LDG streaming), "eig_mode" (0 = cuSOLVER every cycle, 1 = subspace tracking), "sub_min_nao",
- * "overlap", "dist_eig", "panel_stages", "panel_hybrid" (1 = 9-10 column slices run 8 columns on DMMA + 1-2 on the
+ * "overlap" (0 = pass 2 behind the K Gram, 1 = side stream, 3 = same stream with programmatic dependent launch),
+ * "sub_bound" (1 = Lanczos + ||dF||_F spectral bounds, 0 = row sums), "sub_cold" (1 = initial guess by cold-start
+ * subspace iteration, 0 = cuSOLVER), "dist_eig", "panel_stages", "panel_hybrid" (1 = 9-10 column slices run 8 columns on DMMA + 1-2 on the
  * FMA pipe, 0 = padded to 16 DMMA columns), "x_budget_mb", "timers". */
 double nbd_timer_ms(nbd_ctx* ctx, const char* key);
 /* Number of kernels launched by this library since the context was created (bench "gpu_launches"). */

@@ -25,6 +25,8 @@ struct GemmArgs {
   int batch;
   long strideA, strideB, strideC;
   int lower_only;  // 1: compute only tiles with tile_col <= tile_row (square tiles)
+  int pdl;         // host only: launch with programmatic stream serialization (may start while the preceding kernel
+                   // of the stream still runs, once that kernel has signalled launch_dependents; no data dependency)
 };
 
 constexpr int GEMM_BK = 16;
@@ -227,6 +229,19 @@ inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g) {
     attr_set = true;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch > 0 ? g.batch : 1);
+  if (g.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, g);
+  }
   kern<<<grid, NT, SMEM, st>>>(g);
   return cudaGetLastError();
 }

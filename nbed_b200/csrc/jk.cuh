@@ -569,6 +569,9 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
     mbar_fence_init();
   }
   __syncthreads();
+  // every CTA of this grid is resident from the start: a kernel launched behind it with programmatic stream
+  // serialization (the K Gram, no data dependency) may now be scheduled into what is left of the SMs
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long nitems = (long)ntiles * nsplit;  // item = (split, tile): consecutive items are consecutive tiles
   if (warp == JP_CONSUMERS) {
     if (lane == 0) {

@@ -10,6 +10,7 @@
 #include <array>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <future>
 
 #include "common.cuh"
@@ -191,13 +192,13 @@ static inline dim3 grid1(long cnt, int block) { return dim3((unsigned)((cnt + bl
 // ------------------------------------------------------------------------------------------------
 static void gemm(nbd_ctx* c, int M, int N, int K, const double* A, long a_is, long a_ks, const double* B, long b_js,
                  long b_ks, double* C, long ldc, double alpha, double beta, int batch = 1, long sA = 0, long sB = 0,
-                 long sC = 0, int lower = 0) {
+                 long sC = 0, int lower = 0, int pdl = 0) {
   GemmArgs g{};
   g.M = M; g.N = N; g.K = K;
   g.A = A; g.a_is = a_is; g.a_ks = a_ks;
   g.B = B; g.b_js = b_js; g.b_ks = b_ks;
   g.C = C; g.ldc = ldc; g.alpha = alpha; g.beta = beta;
-  g.batch = batch; g.strideA = sA; g.strideB = sB; g.strideC = sC; g.lower_only = lower;
+  g.batch = batch; g.strideA = sA; g.strideB = sB; g.strideC = sC; g.lower_only = lower; g.pdl = pdl;
   NBD_CUDA(launch_gemm(c->stream, g, c->gemm_variant, &c->launches, c->sm_count, c->gemm_tile));
 }
 // C[M][N] = alpha * A[M][K] * B[K][N] + beta * C   (all row-major, leading dimensions given)
@@ -416,7 +417,9 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
   std::vector<std::pair<int, int>> cols;
   if (d_K) for (auto& g : kgroups) cols.push_back({g.c0, g.c1});
   else cols.push_back({0, Ntot});
-  auto j_pass = [&](cudaStream_t st) {
+  // `behind` (optional) is issued directly behind the pass-2 kernel, before the partials are reduced: the K Gram of
+  // the programmatic-launch mode below
+  auto j_pass = [&](cudaStream_t st, const std::function<void()>& behind = nullptr) {
     StageScope ts(c->timers, st, "jk_j");
     const long E = (long)c->ntiles * TILE_ELEMS, E2 = E / 2;
     dim3 gf((n + 127) / 128, n);
@@ -444,6 +447,7 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
         else
           j_pass_tma_kernel<1><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter);
         LAUNCH_CHECK(c);
+        if (behind && s0 == 0) behind();
         j_finalize_kernel<<<gf, 128, 0, st>>>(part, c->d_inv.p, d_J + (long)s0 * nn, n, c->nb, E, nsplit, ns);
         LAUNCH_CHECK(c);
       }
@@ -466,7 +470,7 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
       LAUNCH_CHECK(c);
     }
   };
-  bool forked = false;
+  bool forked = false, pair_done = false;
   for (int p0 = 0; p0 < naux; p0 += chunk) {
     const int np = std::min(chunk, naux - p0);
     const bool last = p0 + np >= naux;
@@ -493,10 +497,9 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
         forked = true;
       }
     }
-    if (d_K) {
-      StageScope ts(c->timers, c->stream, "jk_k");
-      // K_s (+)= alpha * X_g^T X_g with X_g the dense [np * w][n_ld] matrix of group g; consecutive groups of
-      // identical width / sign that feed consecutive sets go out as one batched launch
+    // K_s (+)= alpha * X_g^T X_g with X_g the dense [np * w][n_ld] matrix of group g; consecutive groups of
+    // identical width / sign that feed consecutive sets go out as one batched launch
+    auto k_gram = [&](bool pdl_first) {
       size_t gi = 0;
       while (gi < kgroups.size()) {
         const KGroup& g0 = kgroups[gi];
@@ -510,20 +513,37 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
           const double* Xa = X + L.group_base[gi];
           const long gstride = (long)np * w * n_ld;  // equal-width groups are laid out back to back
           gemm(c, n, n, np * w, Xa, 1, n_ld, Xa, 1, n_ld, d_K + (long)g0.set * nn, n, g0.alpha,
-               k_started[g0.set] ? 1.0 : 0.0, batch, gstride, gstride, nn, /*lower=*/1);
+               k_started[g0.set] ? 1.0 : 0.0, batch, gstride, gstride, nn, /*lower=*/1, /*pdl=*/pdl_first ? 1 : 0);
+          pdl_first = false;
           for (size_t q = gi; q < gj; ++q) k_started[kgroups[q].set] = true;
         }
         gi = gj;
       }
+    };
+    if (fork && c->overlap == 3 && c->jpass_variant == 0 && njset <= 2) {
+      // Option "overlap" = 3 (experiment, not the default): programmatic dependent launch.  Pass 2 (2 CTAs per SM, all
+      // resident at once) signals launch_dependents as soon as its CTAs are up, and the Gram - launched behind it in
+      // the SAME stream with programmatic serialization - gets what is left of each SM (one 57 KiB CTA).  Measured on
+      // B200 (tools/pdl_probe.cu shows the mechanism itself overlaps two grids): the pair then takes 7.9 ms, the same
+      // as back to back - with pass 2 at full speed a lone Gram CTA per SM makes next to no progress, i.e. the two
+      // kernels compete for the L2 -> SM path (31.7 GB + 10.7 GB at ~8 TB/s is a 5.2 ms floor for the pair) and the
+      // placement only decides who starves.  The two-stream mode (6.5 ms) stays the default.
+      // No event may sit between the two launches, so the pair is timed as one stage ("jk_j"; "jk_k" reads 0).
+      j_pass(c->stream, [&] { k_gram(true); });
+      forked = false;
+      pair_done = true;
+    } else if (d_K) {
+      StageScope ts(c->timers, c->stream, "jk_k");
+      k_gram(false);
     }
-    if (fork && !forked) {
+    if (fork && !forked && !pair_done) {
       NBD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
       j_pass(c->stream2);
       NBD_CUDA(cudaEventRecord(c->ev_join, c->stream2));
       forked = true;
     }
   }
-  if (d_J && !forked) j_pass(c->stream);
+  if (d_J && !forked && !pair_done) j_pass(c->stream);
   if (forked) NBD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   if (d_K) symmetrize_lower(c, d_K, n, nkset);
 }
