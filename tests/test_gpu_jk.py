@@ -124,3 +124,38 @@ def test_jk_and_ao2mo_fuzz_small_shapes(ctx):
         got = ctx.ao2mo(c[0], c[1])
         want = nr.two_body_integrals(b, c, restricted=False)
         assert np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), (n, naux)
+
+
+def test_jk_overlap_modes_are_bit_identical(ctx):
+    """Pass 2 behind the Gram (0), next to it on the side stream (1, default) or launched in front of it with
+    programmatic stream serialization (3): scheduling only, the sums are taken in the same order."""
+    n, naux, nocc = 300, 24, (5, 5)
+    rng = np.random.default_rng(11)
+    ctx.load_cderi(_cderi(n, naux))
+    orbs = [rng.normal(size=(n, o)) / np.sqrt(n) for o in nocc]
+    out = {}
+    try:
+        for mode in (1, 0, 3):
+            ctx.set_option("overlap", mode)
+            out[mode] = ctx.jk_orbitals(orbs)
+    finally:
+        ctx.set_option("overlap", 1)
+    for mode in (0, 3):
+        assert np.array_equal(out[mode][0], out[1][0]) and np.array_equal(out[mode][1], out[1][1]), mode
+
+
+def test_jk_hybrid_panel_matches_padded_panel(ctx):
+    """9 / 10 column slices: 8 DMMA columns + 1-2 FMA-pipe columns (default) against the same slices padded to 16 DMMA
+    columns (panel_hybrid = 0).  The FMA columns sum in a different order, so agreement is to rounding, not bitwise."""
+    for n, naux, nocc in [(300, 12, (5, 5)), (1376, 3, (5, 4)), (520, 6, (13, 12))]:
+        rng = np.random.default_rng(n)
+        ctx.load_cderi(_cderi(n, naux))
+        orbs = [rng.normal(size=(n, o)) / np.sqrt(n) for o in nocc]
+        vj1, vk1 = ctx.jk_orbitals(orbs)
+        ctx.set_option("panel_hybrid", 0)
+        try:
+            vj0, vk0 = ctx.jk_orbitals(orbs)
+        finally:
+            ctx.set_option("panel_hybrid", 1)
+        scale = max(1.0, np.abs(vk0).max(), np.abs(vj0).max())
+        assert np.abs(vj1 - vj0).max() <= 1e-13 * scale and np.abs(vk1 - vk0).max() <= 1e-13 * scale

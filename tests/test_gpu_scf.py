@@ -232,3 +232,34 @@ def test_huzinaga_embed_driver_wrapper(ctx):
     assert np.abs(v1 - v0).max() < 1e-7 and np.abs(gpu.get_hcore() - cpu.get_hcore()).max() < 1e-7
     assert np.array_equal(gpu.mo_occ, cpu.mo_occ) and np.abs(gpu.mo_energy - cpu.mo_energy).max() < 1e-8
     assert gpu.get_hcore().shape == (2, p.n, p.n)
+
+
+def test_subspace_start_and_bound_options_agree(ctx):
+    """The cold start of the tracked block (no library eigensolve for the initial guess) and the Lanczos / ||dF||_F
+    spectral bounds change how the occupied eigenvectors are found, not what they are: same iterates as the
+    cuSOLVER-seeded, row-sum-bounded solver, and the cold path really is taken by default."""
+    n, naux, nocc, n_env = 320, 24, 6, 10
+    p = syn.make_problem(n=n, naux=naux, nocc=nocc, n_env=n_env, seed=3, scale=3.0 / np.sqrt(n * naux))
+    ctx.load_cderi(p.cderi())
+    runs = {}
+    try:
+        for cold, bound in ((1, 1), (0, 1), (0, 0)):
+            ctx.set_option("sub_cold", cold)
+            ctx.set_option("sub_bound", bound)
+            ctx.scf_setup(p.nelec, p.ovlp, p.hcore, p.v_emb, p.dm_enviro, NBD_HUZINAGA)
+            c0 = ctx.timer_ms("count:sub_cold_starts")
+            f0 = ctx.timer_ms("count:sub_fallbacks")
+            runs[(cold, bound)] = ctx.huzinaga_scf(30, 1e-8, 1e-6, True)
+            assert (ctx.timer_ms("count:sub_cold_starts") - c0 > 0) == (cold == 1)
+            if cold == 1:
+                assert ctx.timer_ms("count:sub_fallbacks") == f0  # the cold block converged on its own
+    finally:
+        ctx.set_option("sub_cold", 1)
+        ctx.set_option("sub_bound", 1)
+    ref = runs[(0, 0)]
+    for key in ((1, 1), (0, 1)):
+        r = runs[key]
+        assert r[4]["cycles"] == ref[4]["cycles"] and r[4]["converged"] == ref[4]["converged"]
+        k = r[4]["cycles"]
+        assert np.abs(r[4]["trace"][:k, :2] - ref[4]["trace"][:k, :2]).max() < 1e-9
+        assert np.abs(r[2] - ref[2]).max() < 1e-9 and np.abs(r[1] - ref[1]).max() < 1e-9
