@@ -30,6 +30,44 @@ int main() {
     }
     CHECK(res < 1e-12 && orth < 1e-13, "jacobi n=%d residual %.2e orth %.2e", n, res, orth);
   }
+  // Householder + QL eigensolver: same checks, plus agreement with Jacobi, degenerate and already-diagonal inputs
+  for (int n : {1, 2, 3, 7, 10, 16, 32}) {
+    for (int kind = 0; kind < 3; ++kind) {
+      std::vector<double> a((size_t)n * n, 0.0), w, v, wj, vj;
+      if (kind == 0) {
+        for (int i = 0; i < n; ++i)
+          for (int j = 0; j <= i; ++j) a[(size_t)i * n + j] = a[(size_t)j * n + i] = N(rng) * (i == j ? 5.0 : 1.0);
+      } else if (kind == 1) {  // diagonal with repeated entries
+        for (int i = 0; i < n; ++i) a[(size_t)i * n + i] = (double)(i / 2);
+      } else {  // rank-2 plus identity: (n - 2)-fold degenerate eigenvalue
+        std::vector<double> x(n), y(n);
+        for (int i = 0; i < n; ++i) { x[i] = N(rng); y[i] = N(rng); }
+        for (int i = 0; i < n; ++i)
+          for (int j = 0; j < n; ++j) a[(size_t)i * n + j] = (i == j ? 1.0 : 0.0) + x[i] * x[j] - 0.5 * y[i] * y[j];
+      }
+      CHECK(householder_ql_eigh(n, a, w, v), "QL did not converge n=%d kind=%d", n, kind);
+      jacobi_eigh(n, a, wj, vj);
+      double res = 0, orth = 0, scale = 1.0;
+      for (int i = 0; i < n * n; ++i) scale = std::max(scale, std::fabs(a[i]));
+      for (int k = 0; k < n; ++k) {
+        for (int i = 0; i < n; ++i) {
+          double s = 0;
+          for (int j = 0; j < n; ++j) s += a[(size_t)i * n + j] * v[(size_t)j * n + k];
+          res = std::max(res, std::fabs(s - w[k] * v[(size_t)i * n + k]));
+        }
+        for (int l = 0; l < n; ++l) {
+          double s = 0;
+          for (int i = 0; i < n; ++i) s += v[(size_t)i * n + k] * v[(size_t)i * n + l];
+          orth = std::max(orth, std::fabs(s - (k == l ? 1.0 : 0.0)));
+        }
+      }
+      std::sort(w.begin(), w.end());
+      std::sort(wj.begin(), wj.end());
+      double dw = 0;
+      for (int k = 0; k < n; ++k) dw = std::max(dw, std::fabs(w[k] - wj[k]));
+      CHECK(res < 2e-13 * scale * n && orth < 1e-13 * n && dw < 1e-12 * scale, "QL n=%d kind=%d residual %.2e orth %.2e vs jacobi %.2e", n, kind, res, orth, dw);
+    }
+  }
   // LU solve against a manufactured solution, with a zero leading pivot (the bordered DIIS matrix has H[0][0] = 0)
   {
     const int n = 5;
