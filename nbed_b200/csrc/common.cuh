@@ -120,4 +120,15 @@ constexpr int TILE_ELEMS = TILE * TILE;
 constexpr int TILE_BYTES = TILE_ELEMS * 8;
 __host__ __device__ __forceinline__ int tile_swz(int r, int c) { return r * TILE + (c ^ ((r & 3) << 2)); }
 
+// Function attributes (dynamic shared-memory opt-in) are per device: a call site remembers the devices it has
+// configured in a bit mask instead of one process-wide flag, so a process that drives several GPUs stays correct.
+inline bool first_use_on_current_device(unsigned long long& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+  const unsigned long long bit = 1ull << dev;
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 }  // namespace nbd

@@ -222,11 +222,10 @@ inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g) {
   constexpr int SMEM = GEMM_STAGES * (A_ELEMS + B_ELEMS) * 8;
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   auto kern = gemm_dmma_kernel<BM, BN, WM, WN, A_MC, B_NC, VEC>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long configured = 0;
+  if (first_use_on_current_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch > 0 ? g.batch : 1);
   if (g.pdl) {

@@ -431,11 +431,10 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
       nsplit = (naux + rows_per_split - 1) / rows_per_split;
       unsigned int* counter = c->d_jcounter.ensure(4);
       const size_t smem = 256 + (size_t)JP_STAGES * TILE_BYTES;
-      static bool attr_set = false;
-      if (!attr_set) {
+      static unsigned long long configured = 0;
+      if (first_use_on_current_device(configured)) {
         NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
       }
       for (int s0 = 0; s0 < njset; s0 += 2) {
         const int ns = std::min(2, njset - s0);

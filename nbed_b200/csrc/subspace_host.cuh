@@ -189,11 +189,8 @@ static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double
   }
   dim3 g(nrb, 1, c->nspin);
   constexpr int smem = sub_apply_smem_bytes<KB>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    NBD_CUDA(cudaFuncSetAttribute(sub_apply_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static unsigned long long configured = 0;
+  if (first_use_on_current_device(configured)) NBD_CUDA(cudaFuncSetAttribute(sub_apply_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   sub_apply_kernel<KB><<<g, 128, smem, c->stream>>>(a);
   LAUNCH_CHECK(c);
   ++c->sub_applies;
