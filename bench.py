@@ -340,8 +340,9 @@ def run_b200(args):
         "wall_ms_per_step": wall_ms / args.steps,
         "stages_ms": stages,
         "iters_per_s_excl_eigh": 1e3 / max(1e-9, stages["iter_total"] - stages["eigh"] - stages["eig_sub"]),
-        "eigensolver": {"mode": "Chebyshev-filtered subspace iteration of the occupied block between full cuSOLVER "
-                        "dsyevd solves (first cycle, returned spectrum, fallback)" if sub1[0] > sub0[0] else
+        "eigensolver": {"mode": "Chebyshev-filtered subspace iteration of the occupied block (cold-started from "
+                        "pseudo-random vectors for the initial guess when cold_starts > 0); cuSOLVER dsyevd only for the "
+                        "returned spectrum of nbd_huzinaga_scf and as fallback" if sub1[0] > sub0[0] else
                         "cuSOLVER dsyevd every cycle",
                         "matrix_block_products_per_step": (sub1[0] - sub0[0]) / args.steps,
                         "rayleigh_ritz_per_step": (sub1[1] - sub0[1]) / args.steps,
