@@ -6,8 +6,10 @@
 // per 1376^2 matrix) is the Amdahl term of the iteration, so the cycles in between track the invariant subspace
 // of the KB lowest eigenvectors instead: a scaled Chebyshev polynomial of F' damps everything above the block,
 // followed by Rayleigh-Ritz, until the residuals of the occupied vectors are below 1e-10 (densities and energies
-// then agree with a full diagonalisation far inside the 1e-8 parity tolerance).  cuSOLVER still produces the first
-// block, the final full (C, eps), and is the fallback whenever the filter does not converge.
+// then agree with a full diagonalisation far inside the 1e-8 parity tolerance).  The first block of an SCF starts from
+// pseudo-random vectors (cold start, amplification-capped filter degree); the filter interval comes from a few
+// Lanczos steps and is then widened by ||dF'||_F per cycle.  cuSOLVER still produces the final full (C, eps) and is
+// the fallback whenever the filter does not converge or a Ritz value lands above the assumed upper bound.
 //
 // All kernels are small FP64 CUDA-core kernels over L2-resident data (F' is 15 MB at n = 1376).
 #pragma once
