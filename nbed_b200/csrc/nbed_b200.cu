@@ -828,8 +828,14 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "panel_stages") c->panel_stages = (int)value;
   else if (k == "panel_hybrid") c->panel_hybrid = (int)value;
   else if (k == "panel_warps") {
-    NBD_REQUIRE(value == 8 || value == 16, NBD_ERR_ARG, "panel_warps must be 8 or 16");
-    NBD_REQUIRE(c->Bt == nullptr || (int)value == c->panel_warps, NBD_ERR_STATE, "panel_warps fixes the storage order: set it before nbd_cderi_alloc");
+    if (value != 8 && value != 16) {  // (no exception may cross the C ABI here: this function is not guarded)
+      c->err = "panel_warps must be 8 or 16";
+      return NBD_ERR_ARG;
+    }
+    if (c->Bt != nullptr && (int)value != c->panel_warps) {
+      c->err = "panel_warps fixes the storage order: set it before nbd_cderi_alloc";
+      return NBD_ERR_STATE;
+    }
     c->panel_warps = (int)value;
   }
   else if (k == "jpass_variant") c->jpass_variant = (int)value;
