@@ -55,6 +55,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload: str, world: int, stage: str):
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(f"{workload}/N{world}/{stage}", {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
 FP64_PEAK_TFLOPS = 37.2  # profiles/microbench_r01.md: DMMA m8n8k4 measured on this pool's B200 (= nominal)
 
 
@@ -107,65 +116,93 @@ class ClockSampler:
 # Coupling strength of the synthetic 3-centre tensor (multiples of 1/sqrt(naux * nao)): chosen so that the embedded
 # SCF needs a realistic 10-20 cycles from the core guess; the timed cycles are then cycles of an SCF that is still
 # moving (the per-cycle density change is reported), not repetitions of a converged fixed point.
-COUPLING = float(os.environ.get("NBD_BENCH_COUPLING", "16.0"))
+COUPLING = float(os.environ.get("NBD_BENCH_COUPLING", str(syn.BENCH_COUPLING)))
 CYCLES_PER_SCF = 10  # a new embedded SCF (core guess, huzinaga_scf.py:139-148) starts every 10 timed cycles
 
 
 def build_problem(key: str):
-    cfg = dict(syn.CONFIGS[key])
-    p = syn.make_problem(seed=1, scale=COUPLING / np.sqrt(cfg["n"] * cfg["naux"]), **cfg)
-    return cfg, p
+    return syn.bench_problem(key, COUPLING)
 
 
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle restatement; PySCF is not installable here) on host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_iterations_per_s(key: str, steps: int, naux_sample: int):
-    """Times the oracle's Huzinaga loop on a bounded sample of the aux index and extrapolates J/K linearly in naux.
+class _BudgetSpent(Exception):
+    pass
 
+
+def cpu_iterations_per_s(key: str, min_iters: int, budget_s: float):
+    """Times FULL iterations of the oracle's Huzinaga loop (every aux row, nothing extrapolated) on the host cores.
+
+    The loop is the restated reference loop (oracle/nbed_restatement.py: huzinaga_scf.py:93-206) over the NumPy/OpenBLAS
+    restatement of pyscf's density-fitted get_jk; it runs until at least ``min_iters`` cycles are complete and
+    ``budget_s`` seconds of loop time are used.  The 3-centre tensor is held in host RAM when it fits (as pyscf's
+    in-core cderi would be), otherwise it is regenerated block by block and the generator's time is subtracted.
     Only this function (and --impl reference, which calls it) executes anything under oracle/."""
     from oracle import nbed_restatement as nr
     from oracle import pyscf_restatement as ps
+    from oracle import streamed
 
     # all host threads, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
     cores = os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(cores)
+    blas = "unknown"
     try:
-        from threadpoolctl import threadpool_limits
+        from threadpoolctl import threadpool_info, threadpool_limits
 
         threadpool_limits(limits=cores)
+        blas = ", ".join(sorted({f"{d.get('internal_api')} x{d.get('num_threads')}" for d in threadpool_info()}))
     except Exception:
         pass
     cfg, p = build_problem(key)
-    naux = cfg["naux"]
-    naux_sample = min(naux_sample, naux)
-    b = p.cderi_rows(np.arange(naux_sample))
-    mf = ps.DFUHF(p.ovlp, p.hcore, b, p.nelec, max_cycle=steps, conv_tol=0.0)
-    stamps, jk = [], [0.0]
+    n, naux = cfg["n"], cfg["naux"]
+    tensor_bytes = 8.0 * naux * n * (n + 1) / 2
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    src = streamed.for_problem(p)
+    in_core = avail > 1.5 * tensor_bytes + (8 << 30)
+    t_gen0 = time.perf_counter()
+    if in_core:
+        b = np.empty((naux, n * (n + 1) // 2))
+        for p0 in range(0, naux, 256):
+            b[p0 : p0 + 256] = src[p0 : p0 + 256]
+    else:
+        b = src
+    log(f"CPU arm: tensor {'in host RAM' if in_core else 'streamed'} ({tensor_bytes / 1e9:.1f} GB, {time.perf_counter() - t_gen0:.0f} s), BLAS {blas}")
+    mf = ps.DFUHF(p.ovlp, p.hcore, b, p.nelec, max_cycle=10**6, conv_tol=0.0)
+    stamps, gen = [], []
     inner = mf.get_veff
 
     def timed_veff(*a, **k):
-        t = time.perf_counter()
-        stamps.append(t)
-        out = inner(*a, **k)
-        jk[0] += time.perf_counter() - t
-        return out
+        now = time.perf_counter()
+        if len(stamps) >= 1 + min_iters and now - stamps[0] >= budget_s:
+            raise _BudgetSpent()
+        stamps.append(now)
+        gen.append(getattr(src, "gen_seconds", 0.0))
+        if len(stamps) > 1:
+            log(f"CPU arm: full iteration {len(stamps) - 1}: {stamps[-1] - stamps[-2]:.1f} s")
+        return inner(*a, **k)
 
     mf.get_veff = timed_veff
-    nr.huzinaga_scf(mf, p.v_emb, p.dm_enviro, dm_conv_tol=0.0)
-    t_end = time.perf_counter()
-    cycles = len(stamps)
-    t_loop = t_end - stamps[0]
-    t_jk = jk[0] / cycles
-    t_rest = t_loop / cycles - t_jk
-    t_full = t_jk * (naux / naux_sample) + t_rest
+    try:
+        nr.huzinaga_scf(mf, p.v_emb, p.dm_enviro, dm_conv_tol=0.0)
+    except _BudgetSpent:
+        pass
+    cycles = len(stamps) - 1  # complete loop cycles between the first and the last get_veff
+    t_loop = stamps[-1] - stamps[0]
+    t_gen = 0.0 if in_core else gen[-1] - gen[0]
     return {
-        "iters_per_s": 1.0 / t_full,
-        "t_jk_sample_s": t_jk,
-        "t_rest_s": t_rest,
+        "iters_per_s": cycles / (t_loop - t_gen),
         "cycles": cycles,
-        "sample": f"{cycles} iterations of the oracle loop at n={cfg['n']} on {naux_sample} of {naux} aux rows; "
-                  f"J/K time scaled x{naux / naux_sample:.1f}, the n^3 stages measured in full",
+        "cores": cores,
+        "sample": f"{cycles} FULL iterations of the oracle loop (NumPy/OpenBLAS restatement of the reference loop over "
+                  f"pyscf's DF get_jk) at n={n}, naux={naux} (all aux rows, nothing extrapolated), "
+                  f"{(t_loop - t_gen) / cycles:.1f} s each; tensor {'held in host RAM' if in_core else 'regenerated per block (generator time subtracted)'}; "
+                  f"BLAS threads: {blas}",
     }
 
 
@@ -174,24 +211,35 @@ def run_reference(args):
     if rank != 0:
         return 0
     key, desc = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
+    cfg = dict(syn.CONFIGS[key])
     t0 = time.perf_counter()
-    r = cpu_iterations_per_s(key, max(1, args.steps + args.warmup), args.cpu_sample_rows)
+    # bounded: at least 2 full iterations, then as many as fit ~100 s (the driver's K / W only bound it from above)
+    r = cpu_iterations_per_s(key, min(2, max(1, args.steps)), min(100.0, 30.0 * max(1, args.steps)))
     wall = time.perf_counter() - t0
     line = {
         "impl": "reference",
         "metric": "embedded_scf_iterations_per_s", "value": r["iters_per_s"], "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["iters_per_s"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "note": "PySCF is not installed on this image: the CPU arm is the NumPy/OpenBLAS "
-                   "restatement of the reference algorithm (oracle/), density-fitted like the GPU arm"},
-        "cpu_baseline": {"value": r["iters_per_s"], "unit": "iterations/s", "cores": cores, "kind": "port",
+        "config": bench_config(desc, cfg, args.gpus, args.option),
+        "reference_note": "PySCF is not installed on this image: the CPU arm is the NumPy/OpenBLAS restatement of the "
+                          "reference algorithm (oracle/), density-fitted like the GPU arm; it ignores --gpus",
+        "cpu_baseline": {"value": r["iters_per_s"], "unit": "iterations/s", "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": r["iters_per_s"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def bench_config(desc, cfg, world, options):
+    """The `config` object: identical keys and values in the b200 arm and in the reference arm."""
+    return {"workload": desc, "n": cfg["n"], "naux": cfg["naux"], "nocc_per_spin": cfg["nocc"], "n_env": cfg["n_env"],
+            "sharding": f"aux-index x{world}", "l2": "3-centre tensor (>= 4 GB per rank) exceeds the 126 MB L2: "
+            "every iteration streams it from HBM", "eigensolver": "included in value; reported separately under "
+            "stages_ms.eigh (cuSOLVER dsyevd) and stages_ms.eig_sub (filtered subspace iteration)",
+            **({"options": options} if options else {})}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -313,15 +361,17 @@ def run_b200(args):
         roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": frac_hbm}
     else:
         roof = {"bound": "tensor", "achieved": ach_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": frac_tensor}
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of this
-    # very configuration (profiles/ncu_r01_raw_key_metrics.csv, capture r01e: symm_panel_kernel<6, 1, 2>, 8 DMMA + 2 FMA
-    # columns); other shapes / shard sizes were not captured
-    traffic = 31.991025e9 + 0.401689e9 if (dom == "jk_x" and args.workload == "C4" and world == 1 and not args.option) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, from the committed `ncu --set full`
+    # capture of this workload / shard size (profiles/ncu_traffic.json lists capture file and kernel instance); null
+    # for configurations that were not captured
+    traffic = ncu_traffic(args.workload, world, dom) if not args.option else None
     roof.update({"kernel": {"jk_x": "symm_panel_kernel", "jk_j": "j_pass_tma_kernel", "jk_k": "gemm_dmma_kernel (K Gram)"}[dom],
                  "traffic": traffic, "algorithmic_bytes": kern[dom]["bytes"], "algorithmic_flops": kern[dom]["flops"],
                  "ms_per_launch": stages[dom], "peak_source": peak_src,
                  "other_axis": {"hbm_frac": frac_hbm, "fp64_tensor_frac": frac_tensor,
-                                "fp64_peak_tflops": FP64_PEAK_TFLOPS}})
+                                "fp64_peak_tflops": FP64_PEAK_TFLOPS,
+                                "fp64_peak_source": "builder-measured DMMA m8n8k4 microbenchmark (profiles/microbench_r01.md; "
+                                                    "equals the nominal 148 SM x 128 flop/clk x 1.965 GHz); MEASURED_PEAKS.json has no FP64 figure"}})
     # whole J/K against the two-pass model of SURVEY.md 8(d): max(F/P64, B/BW) / t
     f_jk = 4.0 * naux_loc * n * n + 2 * 4.0 * naux_loc * n * n * cfg["nocc"]
     b_jk = 2 * packed_bytes + 3 * 8.0 * n * n
@@ -332,11 +382,7 @@ def run_b200(args):
         "metric": "embedded_scf_iterations_per_s", "value": 1e3 / ms_per_step, "unit": "iterations/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "n": n, "naux": naux, "nocc_per_spin": cfg["nocc"], "n_env": cfg["n_env"],
-                   "sharding": f"aux-index x{world}", "l2": "3-centre tensor (>= 4 GB per rank) exceeds the 126 MB L2: "
-                   "every iteration streams it from HBM", "eigensolver": "included in value; reported separately under "
-                   "stages_ms.eigh (cuSOLVER dsyevd) and stages_ms.eig_sub (filtered subspace iteration)",
-                   **({"options": args.option} if args.option else {})},
+        "config": bench_config(desc, cfg, world, args.option),
         "wall_ms_per_step": wall_ms / args.steps,
         "stages_ms": stages,
         "iters_per_s_excl_eigh": 1e3 / max(1e-9, stages["iter_total"] - stages["eigh"] - stages["eig_sub"]),
@@ -358,36 +404,89 @@ def run_b200(args):
                          "density_change_per_cycle": ddm_trace},
     }
 
-    # ---- extras on rank 0 at N = 1: end-to-end through the host API, ao2mo GB/s, CPU baseline -------------
-    if world == 1 and not args.no_extras:
+    # ---- extras at every N: end-to-end through the host API, sharded ao2mo, the other J/K call sites, mu path -----
+    line["checksum"] = {"energy_last_step": [float(x) for x in e], "norm_ddm_last_step": float(nd),
+                        "what": "per-spin energies and max_s |dD_s|_F after the last timed cycle: every N runs the same "
+                                "deterministic SCFs, so these agree across N to ~1e-10"}
+    if not args.no_extras:
         from nbed_b200.scf import B200UHF, huzinaga_scf
+
+        def wall_max(fn, repeat=1):
+            best = None
+            for _ in range(repeat):
+                barrier()
+                ta = time.perf_counter()
+                out = fn()
+                dt = max_over_ranks(time.perf_counter() - ta)
+                best = dt if best is None else min(best, dt)
+            return best, out
 
         mf = B200UHF(ctx, p.ovlp, p.hcore, p.nelec, max_cycle=args.steps, conv_tol=0.0)
         huzinaga_scf(mf, p.v_emb, p.dm_enviro, dm_conv_tol=0.0)  # warm
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        out = huzinaga_scf(mf, p.v_emb, p.dm_enviro, dm_conv_tol=0.0)
-        t_e2e = time.perf_counter() - t0
+        t_e2e, out = wall_max(lambda: huzinaga_scf(mf, p.v_emb, p.dm_enviro, dm_conv_tol=0.0))
         nn8 = 8 * n * n
         line["e2e"] = {"value": args.steps / t_e2e, "unit": "iterations/s",
                        "h2d_bytes_per_step": (2 + 2 + 2) * nn8 / args.steps,
                        "d2h_bytes_per_step": (2 * 3 * nn8 + 2 * 8 * n) / args.steps + 8 * 8,
-                       "what": "nbed_b200.scf.huzinaga_scf(scf_method, v_emb, dm_env) with host NumPy inputs/outputs, "
-                               f"{args.steps} cycles per call (S, h, V, gamma H2D; per-cycle scalars D2H; C, eps, D, Huz D2H)"}
-        del out
+                       "what": "nbed_b200.scf.huzinaga_scf(scf_method, v_emb, dm_env) with host NumPy inputs/outputs on every rank, "
+                               f"{args.steps} cycles per call (S, h, V, gamma H2D; per-cycle scalars D2H; C, eps, D, Huz D2H), wall clock, max over ranks"}
+        c_last, e_last, dm_last = out[0], out[1], out[2]
+        line["checksum"]["e2e_trace_dm_s"] = [float(np.einsum("ij,ji->", dm_last[s_], p.ovlp)) for s_ in range(2)]
         log(f"e2e host-API run: {t_e2e * 1e3:.1f} ms for {args.steps} cycles")
-        # ao2mo at the C5 shape (BASELINE configs[4]): m = 40 per spin
+
+        # the driver's other J/K call sites (driver.py:344-345,391,847-849,627; concentric.py:95): get_veff with the
+        # FULL-system density (all n_env + nocc occupied orbitals per spin) on the same device tensor
+        if key.startswith("C4"):
+            nfull = cfg["nocc"] + cfg["n_env"]
+            occ = np.zeros((2, n))
+            occ[:, :nfull] = 1.0
+            w_, v_ = np.linalg.eigh(p.ovlp)
+            xs = (v_ / np.sqrt(w_)) @ v_.T
+            _, cfull = np.linalg.eigh(xs @ p.hcore @ xs)
+            cfull = np.array([xs @ cfull] * 2)
+            dm_full = mf.make_rdm1(cfull, occ)
+            mf.get_veff(dm=dm_full)
+            t_v, vfull = wall_max(lambda: mf.get_veff(dm=dm_full), 2)
+            dev_ms = ctx.timer_ms("jk_total")
+            fl = 4.0 * naux * n * n + 2 * 4.0 * naux * n * n * nfull
+            line["full_system_veff"] = {
+                "what": f"B200UHF.get_veff(dm) with {nfull} occupied orbitals per spin (the embedding set-up's J/K builds), host in/out",
+                "wall_ms": t_v * 1e3, "device_ms_rank0": dev_ms, "tflops_device": fl / world / (dev_ms * 1e-3) / 1e12,
+                "fp64_tensor_frac": fl / world / (dev_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                "stages_ms": {k: ctx.timer_ms(k) for k in ("jk_x", "jk_rho", "jk_j", "jk_k", "allreduce")},
+                "checksum_trace_vhf_dm": float(np.einsum("sij,sji->", vfull, np.asarray(dm_full)))}
+            log(f"full-system get_veff: wall {t_v * 1e3:.1f} ms, device {dev_ms:.1f} ms")
+
+            # mu-shift projector path (BASELINE config 1's projector, driver.py:500-538) at this shape: per-cycle time
+            from nbed_b200.backend import NBD_MU_SHIFT
+
+            dm0 = np.array([cfull[s_][:, : cfg["nocc"]] @ cfull[s_][:, : cfg["nocc"]].T for s_ in range(2)])
+            ctx.scf_setup(p.nelec, p.ovlp, p.hcore, p.v_emb, p.dm_enviro, NBD_MU_SHIFT, 1e6)
+            ncyc = 4
+            ctx.mu_scf(ncyc, 0.0, 0.0, dm0)
+            barrier()
+            _, _, _, _, _, info_mu = ctx.mu_scf(ncyc, 0.0, 0.0, dm0)
+            mu_ms = max_over_ranks(ctx.timer_ms("iter_total")) / ncyc
+            line["mu_shift"] = {"what": "nbd_mu_scf (pyscf kernel() semantics: CDIIS, dsygvd per spin, J/K) at this shape, mu = 1e6",
+                                "cycles": ncyc, "ms_per_cycle": mu_ms, "iterations_per_s": 1e3 / mu_ms,
+                                "stages_ms_per_cycle": {k: ctx.timer_ms(k) / ncyc for k in ("jk_total", "eigh", "diis", "fock", "energy", "density")},
+                                "e_tot": info_mu["e_tot"]}
+            log(f"mu-shift path: {mu_ms:.2f} ms per cycle")
+
+        # ao2mo at the C5 shape (BASELINE configs[4]): m = 40 per spin, aux-sharded like the SCF, one all-reduce of 3 m^4
         c5, p5 = build_problem("C5_h2o16_def2tzvp")
-        ctx.cderi_alloc(c5["n"], c5["naux"])
-        ctx.cderi_synth(p5.seed, p5.scale, 0)
+        lo5, hi5 = aux_shard(c5["naux"], rank, world)
+        ctx.cderi_alloc(c5["n"], hi5 - lo5)
+        ctx.cderi_synth(p5.seed, p5.scale, lo5)
         mo = syn.random_orthonormal_mos(p5.ovlp, c5["m"], 0)
         ctx.ao2mo(mo[0], mo[1])
         ao_ms, ao_dev = [], []
         for _ in range(3):
+            barrier()
             ta = time.perf_counter()
-            ctx.ao2mo(mo[0], mo[1])  # host C in, host (4, m, m, m, m) out: H2D / D2H inside the timed region
-            ao_ms.append((time.perf_counter() - ta) * 1e3)
-            ao_dev.append(ctx.timer_ms("ao2mo_total"))
+            eri = ctx.ao2mo(mo[0], mo[1])  # host C in, host (4, m, m, m, m) out: H2D / D2H inside the timed region
+            ao_ms.append(max_over_ranks(time.perf_counter() - ta) * 1e3)
+            ao_dev.append(max_over_ranks(ctx.timer_ms("ao2mo_total")))
         ao_t = min(ao_ms) * 1e-3
         log(f"ao2mo: wall {ao_ms} ms, device {ao_dev} ms")
         m = c5["m"]
@@ -397,20 +496,25 @@ def run_b200(args):
         ctx.build_hamiltonian(h5, mo[0], mo[1])
         t_b = []
         for _ in range(2):
+            barrier()
             tb0 = time.perf_counter()
             ctx.build_hamiltonian(h5, mo[0], mo[1])
-            t_b.append((time.perf_counter() - tb0) * 1e3)
+            t_b.append(max_over_ranks(time.perf_counter() - tb0) * 1e3)
         line["hamiltonian_build"] = {"what": "HamiltonianBuilder.build() as one device call: one-body + 4 two-body blocks + "
                                      "spin-orbital scatter (EQ_TOLERANCE, x0.5); host in (C, hcore), host out (h1, h2 = 328 MB)",
                                      "wall_ms": min(t_b), "device_ms": ctx.timer_ms("build_total")}
-        line["ao2mo"] = {"workload": f"(H2O)16-shaped n={c5['n']} naux={c5['naux']} m={m} UHF", "ms": ao_t * 1e3,
-                         "device_ms": min(ao_dev), "timing": "wall clock around the host-buffer call (ms, gbs, tflops); device_ms = kernels only",
+        dev_t = min(ao_dev) * 1e-3
+        line["ao2mo"] = {"workload": f"(H2O)16-shaped n={c5['n']} naux={c5['naux']} m={m} UHF, aux-sharded x{world}",
+                         "ms": ao_t * 1e3, "device_ms": min(ao_dev),
+                         "timing": "ms / gbs / tflops: wall clock around the host-buffer call, max over ranks; device_*: kernels + all-reduce only",
                          "gbs": b_ao / ao_t / 1e9, "tflops": f_ao / ao_t / 1e12,
-                         "fp64_tensor_frac": f_ao / ao_t / 1e12 / FP64_PEAK_TFLOPS,
-                         "stages_ms": {k: ctx.timer_ms(k) for k in ("ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm")}}
-        if not args.no_cpu:
-            r = cpu_iterations_per_s(key, 3, args.cpu_sample_rows)
-            line["cpu_baseline"] = {"value": r["iters_per_s"], "unit": "iterations/s", "cores": os.cpu_count() or 1,
+                         "device_gbs": b_ao / dev_t / 1e9, "device_tflops": f_ao / dev_t / 1e12,
+                         "fp64_tensor_frac_device": f_ao / dev_t / 1e12 / FP64_PEAK_TFLOPS / world,
+                         "stages_ms": {k: ctx.timer_ms(k) for k in ("ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm", "allreduce")},
+                         "checksum_sum_abs": float(np.abs(eri).sum())}
+        if world == 1 and not args.no_cpu:
+            r = cpu_iterations_per_s(key, 1, 0.0)
+            line["cpu_baseline"] = {"value": r["iters_per_s"], "unit": "iterations/s", "cores": r["cores"],
                                     "kind": "port", "sample": r["sample"]}
     ctx.close()
     if rank == 0:
@@ -433,7 +537,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample-rows", type=int, default=48)
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / ao2mo / cpu_baseline (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--option", action="append", default=[], metavar="KEY=INT", help="nbd_set_option before the run")

@@ -103,6 +103,19 @@ def make_problem(n: int, naux: int, nocc: int, n_env: int, seed: int = 0, scale:
                             (nocc, nocc))
 
 
+# Coupling strength of bench.py's synthetic tensor, in multiples of 1/sqrt(naux * nao): chosen so that the embedded SCF
+# needs a realistic ~10 cycles from the core guess.  The full-size golden fixtures (tests/golden/make_golden_fullsize.py)
+# are generated on exactly this problem, so parity at the stated sizes is parity of the benchmarked workload.
+BENCH_COUPLING = 16.0
+BENCH_SEED = 1
+
+
+def bench_problem(key: str, coupling: float | None = None) -> tuple[dict, SyntheticProblem]:
+    cfg = dict(CONFIGS[key])
+    c = BENCH_COUPLING if coupling is None else float(coupling)
+    return cfg, make_problem(seed=BENCH_SEED, scale=c / np.sqrt(cfg["n"] * cfg["naux"]), **cfg)
+
+
 def random_orthonormal_mos(ovlp: np.ndarray, m: int, seed: int = 0) -> np.ndarray:
     """(2, n, m) S-orthonormal coefficient blocks for the ao2mo tests."""
     rng = np.random.default_rng(seed + 77)

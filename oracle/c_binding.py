@@ -17,7 +17,8 @@ def load(build: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB) and build:
+    stale = os.path.exists(_LIB) and os.path.getmtime(_LIB) < os.path.getmtime(os.path.join(_HERE, "c_kernels.c"))
+    if (stale or not os.path.exists(_LIB)) and build:
         try:
             subprocess.run(["make", "-s", "-C", _HERE], check=True, capture_output=True, timeout=120)
         except Exception:
@@ -29,6 +30,9 @@ def load(build: bool = True):
     lib.oracle_unpack_tril.restype = None
     lib.oracle_df_jk_occ.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.oracle_df_jk_occ.restype = None
+    if hasattr(lib, "oracle_synth_rows"):
+        lib.oracle_synth_rows.argtypes = [C.c_ulonglong, C.c_int, C.c_double, C.c_long, C.c_long, C.c_void_p]
+        lib.oracle_synth_rows.restype = None
     _lib = lib
     return lib
 
@@ -58,3 +62,13 @@ def df_jk_occ(cderi: np.ndarray, orbs):
     lib.oracle_df_jk_occ(cderi.ctypes.data, cderi.shape[0], n, len(orbs), ncol.ctypes.data, flat.ctypes.data,
                          vj.ctypes.data, vk.ctypes.data)
     return vj, vk
+
+
+def synth_rows(seed: int, n: int, scale: float, row0: int, nrows: int) -> np.ndarray | None:
+    """Rows [row0, row0 + nrows) of the synthetic packed tensor (bit-identical to synthetic.synth_cderi_rows)."""
+    lib = load()
+    if lib is None or not hasattr(lib, "oracle_synth_rows"):
+        return None
+    out = np.empty((nrows, n * (n + 1) // 2))
+    lib.oracle_synth_rows(int(seed), int(n), float(scale), int(row0), int(nrows), out.ctypes.data)
+    return out

@@ -114,3 +114,27 @@ void oracle_df_jk_occ(const double* cderi, long naux, int n, int nset, const int
       }
   free(rho);
 }
+
+/* Counter-based synthetic 3-centre tensor of nbed_b200/synthetic.py (SplitMix64 of the packed index), bit-identical to
+ * synthetic.hash_uniform / the device generator: rows [row0, row0 + nrows) of B[P][mu >= nu], packed-lower.  Lets the
+ * oracle stream the 31 GB tensor of BASELINE config 4 block by block, the way pyscf's with_df.loop() feeds
+ * df_jk.get_jk from disk. */
+static inline unsigned long long oracle_splitmix64(unsigned long long x) {
+  unsigned long long z = x + 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+void oracle_synth_rows(unsigned long long seed, int n, double scale, long row0, long nrows, double* out) {
+  const unsigned long long npair = (unsigned long long)n * (n + 1) / 2;
+#pragma omp parallel for schedule(static)
+  for (long r = 0; r < nrows; ++r) {
+    const unsigned long long base = (seed << 48) + (unsigned long long)(row0 + r) * npair;
+    double* dst = out + (unsigned long long)r * npair;
+    for (unsigned long long k = 0; k < npair; ++k) {
+      const unsigned long long z = oracle_splitmix64(base + k);
+      const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+      dst[k] = u * scale;
+    }
+  }
+}

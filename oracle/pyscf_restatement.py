@@ -319,7 +319,8 @@ class DFSCFBase:
     def __init__(self, ovlp, hcore, cderi, nelec, e_nuc=0.0, max_cycle=50, conv_tol=1e-9):
         self._s = np.asarray(ovlp)
         self._h = np.asarray(hcore)
-        self.cderi = np.asarray(cderi)
+        # a row-streamed tensor (oracle/streamed.py) stands in for pyscf's on-disk cderi at sizes that do not fit RAM
+        self.cderi = cderi if getattr(cderi, "rows_are_streamed", False) else np.asarray(cderi)
         self.mol = _Mol(nelec, e_nuc)
         self.max_cycle = max_cycle
         self.conv_tol = conv_tol

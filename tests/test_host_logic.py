@@ -73,6 +73,43 @@ def test_synthetic_tensor_is_counter_based():
     assert p.cderi().shape == (20, 78)
 
 
+def test_streamed_tensor_matches_the_numpy_generator_bit_for_bit():
+    """oracle/streamed.py (C generator behind a row-sliceable object) == synthetic.synth_cderi_rows, and the oracle's
+    J/K over the streamed object == over the materialised array: what the full-size goldens rest on."""
+    from nbed_b200 import synthetic as syn
+    from oracle import pyscf_restatement as ps
+    from oracle import streamed
+
+    p = syn.make_problem(n=37, naux=301, nocc=3, n_env=2, seed=6)
+    st = streamed.for_problem(p)
+    full = p.cderi()
+    assert st.shape == full.shape and len(st) == 301
+    assert np.array_equal(st[0:301], full) and np.array_equal(st[250:999], full[250:]) and np.array_equal(st[7], full[7])
+    rng = np.random.default_rng(0)
+    orbs = [rng.normal(size=(37, 3)), rng.normal(size=(37, 2))]
+    j0, k0 = ps.df_get_jk_occ(full, orbs)
+    j1, k1 = ps.df_get_jk_occ(st, orbs)
+    assert np.array_equal(j0, j1) and np.array_equal(k0, k1)
+    mf = ps.DFUHF(p.ovlp, p.hcore, st, p.nelec)
+    assert mf.cderi is st
+
+
+def test_full_size_goldens_are_committed_and_describe_the_stated_sizes():
+    g4 = np.load(os.path.join(ROOT, "tests", "golden", "c4_fullsize.npz"))
+    g5 = np.load(os.path.join(ROOT, "tests", "golden", "c5_fullsize.npz"))
+    assert (int(g4["n"]), int(g4["naux"])) == (1376, 4128) and int(g4["cycles"]) >= 3
+    assert g4["energies"].shape == (int(g4["cycles"]), 2) and g4["jk_orbitals"].shape == (2, 1376, 5)
+    assert g4["oracle_vs_reference"].max() < 1e-10  # restatement == unmodified reference loop at the full size
+    for name in ("vj", "vk", "dm", "huz"):
+        assert g4[name + "_rows"].shape[-2:] == (43, 1376) and np.isfinite(g4[name + "_fro"]).all()
+    assert (int(g5["n"]), int(g5["naux"]), int(g5["m"])) == (688, 2064, 40)
+    assert g5["two_samples"].shape[0] == 4 and g5["two_samples"].shape[1] > 10000
+    from nbed_b200 import synthetic as syn
+
+    _, p = syn.bench_problem("C4_h2o32_def2tzvp")
+    assert p.scale == float(g4["scale"]) and p.seed == int(g4["seed"])
+
+
 def test_diis_restatement_recovers_linear_fixed_point():
     """pyscf.lib.diis.DIIS on x -> A x + b converges to the fixed point in <= dim + 2 steps."""
     from oracle.pyscf_restatement import DIIS
@@ -89,7 +126,7 @@ def test_diis_restatement_recovers_linear_fixed_point():
 
 def test_bench_reference_arm_emits_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C3",
-                          "--steps", "1", "--warmup", "0", "--cpu-sample-rows", "16"], capture_output=True, text=True,
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
                          timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
@@ -98,6 +135,10 @@ def test_bench_reference_arm_emits_contract_line():
                 "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
+    assert "FULL iterations" in line["cpu_baseline"]["sample"] and "extrapolated" in line["cpu_baseline"]["sample"]
+    # same `config` keys as the GPU arm prints (the driver compares the two)
+    assert {"workload", "n", "naux", "nocc_per_spin", "n_env", "sharding"} <= set(line["config"])
+    assert line["config"]["n"] == 174 and line["config"]["naux"] == 522
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
 
 
