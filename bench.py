@@ -291,6 +291,8 @@ def run_b200(args):
         return float(t.item())
 
     ctx.scf_setup(p.nelec, p.ovlp, p.hcore, p.v_emb, p.dm_enviro, NBD_HUZINAGA)
+    # the localizer hands over c_enviro next to dm_enviro = c_enviro c_enviro^T (localizers/system.py:33): rank-r projector
+    ctx.scf_set_env_orbitals(p.c_env)
     ctx.scf_bench_init()
     log("static set-up and initial guess done")
     sampler = ClockSampler(local) if rank == 0 else None  # started early: nvidia-smi needs ~1 s to deliver samples
@@ -421,15 +423,20 @@ def run_b200(args):
                 best = dt if best is None else min(best, dt)
             return best, out
 
+        from nbed_b200 import LocalizedSystem
+
         mf = B200UHF(ctx, p.ovlp, p.hcore, p.nelec, max_cycle=args.steps, conv_tol=0.0)
-        huzinaga_scf(mf, p.v_emb, p.dm_enviro, dm_conv_tol=0.0)  # warm
-        t_e2e, out = wall_max(lambda: huzinaga_scf(mf, p.v_emb, p.dm_enviro, dm_conv_tol=0.0))
+        # the reference's caller (driver.py:576-589) passes localized_system.dm_enviro; the mirror's carries c_enviro
+        lsys = LocalizedSystem(np.arange(cfg["nocc"]), np.arange(cfg["n_env"]), p.c_env[:, :, :0], p.c_env, p.c_env)
+        assert np.array_equal(np.asarray(lsys.dm_enviro), p.dm_enviro)
+        huzinaga_scf(mf, p.v_emb, lsys.dm_enviro, dm_conv_tol=0.0)  # warm
+        t_e2e, out = wall_max(lambda: huzinaga_scf(mf, p.v_emb, lsys.dm_enviro, dm_conv_tol=0.0))
         nn8 = 8 * n * n
         line["e2e"] = {"value": args.steps / t_e2e, "unit": "iterations/s",
-                       "h2d_bytes_per_step": (2 + 2 + 2) * nn8 / args.steps,
+                       "h2d_bytes_per_step": ((2 + 2 + 2) * nn8 + 2 * 8 * n * cfg["n_env"]) / args.steps,
                        "d2h_bytes_per_step": (2 * 3 * nn8 + 2 * 8 * n) / args.steps + 8 * 8,
                        "what": "nbed_b200.scf.huzinaga_scf(scf_method, v_emb, dm_env) with host NumPy inputs/outputs on every rank, "
-                               f"{args.steps} cycles per call (S, h, V, gamma H2D; per-cycle scalars D2H; C, eps, D, Huz D2H), wall clock, max over ranks"}
+                               f"{args.steps} cycles per call (S, h, V, gamma, c_enviro H2D; per-cycle scalars D2H; C, eps, D, Huz D2H), wall clock, max over ranks"}
         c_last, e_last, dm_last = out[0], out[1], out[2]
         line["checksum"]["e2e_trace_dm_s"] = [float(np.einsum("ij,ji->", dm_last[s_], p.ovlp)) for s_ in range(2)]
         log(f"e2e host-API run: {t_e2e * 1e3:.1f} ms for {args.steps} cycles")

@@ -43,7 +43,8 @@ int nbd_set_option(nbd_ctx* ctx, const char* key, long value);
  *       "eigh" (cuSOLVER), "eig_sub" (filtered subspace iteration), "eig_bcast", "density", "energy", "iter_total",
  *       "scf_total", "ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm", "ao2mo_total", "spinorb", "build_total".
  * Cumulative counters since context creation: "count:sub_applies", "count:sub_outer", "count:sub_fallbacks",
- * "count:sub_cold_starts", "count:sub_lanczos".
+ * "count:sub_cold_starts", "count:sub_lanczos", "count:sub_rejects" (SCF runs redone with cuSOLVER because the tracked
+ * block's Ritz values disagreed with the final full spectrum).
  * Options of nbd_set_option: "jk_variant", "gemm_variant" (1 = simple reference kernels), "jpass_variant"
  * (0 = TMA-fed, 1 = LDG streaming), "eig_mode" (0 = cuSOLVER every cycle, 1 = subspace tracking), "sub_min_nao",
  * "overlap" (0 = pass 2 behind the K Gram, 1 = side stream, 3 = same stream with programmatic dependent launch),
@@ -105,6 +106,13 @@ int nbd_scf_setup(nbd_ctx* ctx, int nspin, const int* nelec, const double* ovlp,
  * nbed/scf/huzinaga_scf.py:96,133-136 and the second term of get_huzinaga_operator :82-88; built by the PAO
  * localizer in nbed/driver.py:566-575).  dm_env_virt [nspin][nao][nao], NULL switches it off.  After nbd_scf_setup. */
 int nbd_scf_set_virtual_projector(nbd_ctx* ctx, const double* dm_env_virt);
+
+/* Optional low-rank factor of the occupied environment density: dm_env[s] = c_env[s] c_env[s]^T, c_env host
+ * [nspin][nao][r] - the localizer's c_enviro (nbed/localizers/system.py:33 builds dm_enviro from exactly this product).
+ * With it the projector product F gamma S of get_huzinaga_operator (nbed/scf/huzinaga_scf.py:77) runs as two rank-r
+ * GEMMs (4 n^2 r flop instead of 2 n^3).  The factor is verified on the device against the dm_env of nbd_scf_setup;
+ * NBD_ERR_ARG (and the dense product stays in use) when it does not reproduce it.  After nbd_scf_setup. */
+int nbd_scf_set_env_orbitals(nbd_ctx* ctx, int r, const double* c_env);
 
 typedef struct nbd_scf_result {
   int converged;      /* conv flag                                              */

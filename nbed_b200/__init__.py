@@ -4,3 +4,4 @@ from .backend import NBD_HUZINAGA, NBD_MU_SHIFT, B200Context, NbdError  # noqa: 
 from .ham_builder import HamiltonianBuilder, reduce_virtuals  # noqa: F401
 from .scf import (B200RHF, B200UHF, energy_elec, get_huzinaga_operator, huzinaga_embed, huzinaga_scf,  # noqa: F401
                   mu_embed)
+from .localized_system import LocalizedSystem  # noqa: F401,E402

@@ -17,7 +17,7 @@ NBD_MU_SHIFT = 1
 EXPORTS = [
     "nbd_version", "nbd_create", "nbd_destroy", "nbd_last_error", "nbd_set_option", "nbd_timer_ms",
     "nbd_launch_count", "nbd_host_alloc", "nbd_host_free", "nbd_comm_unique_id", "nbd_comm_init", "nbd_cderi_alloc", "nbd_cderi_upload",
-    "nbd_cderi_synth", "nbd_cderi_download", "nbd_jk", "nbd_jk_dm", "nbd_scf_setup", "nbd_scf_set_virtual_projector", "nbd_huzinaga_scf",
+    "nbd_cderi_synth", "nbd_cderi_download", "nbd_jk", "nbd_jk_dm", "nbd_scf_setup", "nbd_scf_set_virtual_projector", "nbd_scf_set_env_orbitals", "nbd_huzinaga_scf",
     "nbd_mu_scf", "nbd_scf_bench_init", "nbd_scf_bench_iteration", "nbd_ao2mo", "nbd_one_body",
     "nbd_spinorb_from_spatial", "nbd_build_hamiltonian",
 ]
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
         "nbd_jk_dm": (I, [P, I, P, P, P]),
         "nbd_scf_setup": (I, [P, I, P, P, P, P, P, I, D]),
         "nbd_scf_set_virtual_projector": (I, [P, P]),
+        "nbd_scf_set_env_orbitals": (I, [P, I, P]),
         "nbd_huzinaga_scf": (I, [P, I, D, D, I, P, P, P, P, P, P, C.POINTER(ScfResult)]),
         "nbd_mu_scf": (I, [P, I, D, D, P, P, P, P, P, P, P, C.POINTER(ScfResult)]),
         "nbd_scf_bench_init": (I, [P]),

@@ -133,13 +133,38 @@ class B200Context:
 
     # -- embedded SCF ---------------------------------------------------------------------------
     def scf_setup(self, nelec, ovlp, hcore, v_emb, dm_env, projector: int, mu: float = 0.0):
-        v_emb, dm_env = f64(v_emb), f64(dm_env)
-        assert v_emb.ndim == dm_env.ndim and v_emb.ndim in (2, 3)
+        """``hcore`` may be (n, n) or - once ``get_hcore`` has been patched by a previous embedding
+        (nbed/driver.py:529,597) - spin-resolved (nspin, n, n); the reference simply broadcasts
+        ``get_hcore() + embedding_potential`` (huzinaga_scf.py:140,157), so the spin-resolved part is folded into the
+        potential with the same host addition and the C-ABI receives a zero (n, n) core Hamiltonian."""
+        v_emb, dm_env, ovlp, hcore = f64(v_emb), f64(dm_env), f64(ovlp), f64(hcore)
+        n = self.nao
+        if v_emb.ndim != dm_env.ndim or v_emb.ndim not in (2, 3):
+            raise ValueError("v_emb / dm_env must both be (n, n) or both (2, n, n)")
         nspin = 1 if v_emb.ndim == 2 else 2
+        want = (n, n) if nspin == 1 else (2, n, n)
+        if ovlp.shape != (n, n) or v_emb.shape != want or dm_env.shape != want:
+            raise ValueError(f"shape mismatch: ovlp {ovlp.shape}, v_emb {v_emb.shape}, dm_env {dm_env.shape}; the device "
+                             f"tensor has nao = {n}")
+        if hcore.shape == want and nspin == 2:
+            v_emb, hcore = f64(hcore + v_emb), np.zeros((n, n))
+        elif hcore.shape != (n, n):
+            raise ValueError(f"hcore has shape {hcore.shape}; expected ({n}, {n}) or {want}")
         ne = np.array(list(nelec), dtype=np.int32)
+        if ne.shape != (2,):
+            raise ValueError("nelec must be (n_alpha, n_beta)")
         self._nspin = nspin
-        self._ck(self._lib.nbd_scf_setup(self._h, nspin, ptr(ne), ptr(f64(ovlp)), ptr(f64(hcore)), ptr(v_emb),
+        self._ck(self._lib.nbd_scf_setup(self._h, nspin, ptr(ne), ptr(ovlp), ptr(hcore), ptr(v_emb),
                                          ptr(dm_env), int(projector), float(mu)))
+
+    def scf_set_env_orbitals(self, c_env):
+        """Low-rank factor of the environment density (dm_env = c_env c_env^T, shape (n, r) or (2, n, r))."""
+        n, ns = self.nao, self._nspin
+        c_env = f64(c_env)
+        r = c_env.shape[-1]
+        if c_env.shape != ((n, r) if ns == 1 else (2, n, r)):
+            raise ValueError(f"c_env has shape {c_env.shape}")
+        self._ck(self._lib.nbd_scf_set_env_orbitals(self._h, int(r), ptr(c_env)))
 
     def scf_set_virtual_projector(self, dm_env_virt):
         n, ns = self.nao, self._nspin

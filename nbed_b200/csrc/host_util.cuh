@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 #include <cstdarg>
 #include <cstdio>
 #include <map>
@@ -132,13 +133,16 @@ struct StageScope {
   bool on;
   StageScope(StageTimers& timers, cudaStream_t stream, const char* key) : t(&timers), st(stream), on(timers.enabled) {
     if (!on) return;
+    nvtxRangePushA(key);  // same names as the nbd_timer_ms keys: `ncu --nvtx --nvtx-include "jk_x/"` selects a stage
     StageTimers::Rec r{key, t->get(), t->get()};
     cudaEventRecord(r.a, st);
     t->open.push_back(r);
     idx = t->open.size() - 1;
   }
   ~StageScope() {
-    if (on) cudaEventRecord(t->open[idx].b, st);
+    if (!on) return;
+    cudaEventRecord(t->open[idx].b, st);
+    nvtxRangePop();
   }
 };
 

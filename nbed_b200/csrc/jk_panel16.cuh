@@ -104,7 +104,7 @@ inline PanelPlan build_panel_plan_w(int nb, int S, const std::vector<int>& seq, 
 
 constexpr int XK16_CONSUMER_WARPS = 16;
 constexpr int XK16_THREADS = (XK16_CONSUMER_WARPS + 4) * 32;
-constexpr int XK16_CONSUMER_REGS = 120;  // 512 * 120 + 128 * 24 = 64512 <= 65536
+constexpr int XK16_CONSUMER_REGS = 112;  // setmaxnreg only moves registers INSIDE the CTA allocation (640 x 96 at launch): the 4 producer warps release 128 x (96 - 24) = 9216, the 16 consumer warps may take 512 x (112 - 96) = 8192; asking for 120 (12288) blocks forever (the hang of the first GPU run, profiles/r02_panel16.md)
 constexpr int XK16_PRODUCER_REGS = 24;
 
 // Sum the four tq lanes' partials pf[mi] (mi = 0..3) so that lane tq ends up with the total of mi = 2 (tq & 1) + (tq >> 1).

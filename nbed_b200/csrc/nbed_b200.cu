@@ -102,6 +102,17 @@ struct PlanDev {
   DBuf<int> begin;
 };
 
+struct KGroup {
+  int set;       // which K matrix
+  int c0, c1;    // columns [c0, c1) of the orbital block
+  double alpha;  // +1 / -1 (signed eigen-factors of a dense density)
+};
+// state of a Huzinaga loop between iterations: the staged orbital block of the next J/K
+struct HuzLoop {
+  int Ntot = 0;
+  std::vector<KGroup> groups;
+};
+
 struct nbd_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -173,9 +184,13 @@ struct nbd_ctx {
   bool sub_bounds_valid = false, sub_is_cold = false;
   double sub_up[2] = {0, 0}, sub_low[2] = {0, 0}, sub_up_ref[2] = {0, 0}, sub_low_ref[2] = {0, 0};
   DBuf<unsigned int> sTicket;
+  long sub_rejects = 0;  // SCF runs redone with the library eigensolver because the tracked block failed the final check
+  // low-rank form of the occupied environment projector: gamma_s = V_s V_s^T (nbd_scf_set_env_orbitals)
+  int env_rank = 0;
+  DBuf<double> envV, envZ, envW;  // V rows [ns][r][n];  Z = V^T S [ns][r][n];  W = F V [ns][n][r]
   // bench state
   bool bench_ready = false;
-  double bench_eprev[2] = {0, 0};
+  HuzLoop bench_loop;
 
   // ---- ao2mo ----
   DBuf<double> mo_c, Lbuf, eri, eri_phys;
@@ -236,12 +251,6 @@ static void all_reduce(nbd_ctx* c, double* buf, size_t count) {
 // ------------------------------------------------------------------------------------------------
 // J/K on device-resident orbitals
 // ------------------------------------------------------------------------------------------------
-struct KGroup {
-  int set;       // which K matrix
-  int c0, c1;    // columns [c0, c1) of the orbital block
-  double alpha;  // +1 / -1 (signed eigen-factors of a dense density)
-};
-
 template <int NSLOT, int NB, int NF = 0>
 static void launch_symm_panel(nbd_ctx* c, const XArgs& a, int grid, size_t smem) {
   auto kern = symm_panel_kernel<NSLOT, NB, NF>;
@@ -856,6 +865,7 @@ double nbd_timer_ms(nbd_ctx* c, const char* key) {
   if (!strcmp(key, "count:sub_fallbacks")) return (double)c->sub_fallbacks;
   if (!strcmp(key, "count:sub_lanczos")) return (double)c->sub_lanczos;
   if (!strcmp(key, "count:sub_cold_starts")) return (double)c->sub_cold_starts;
+  if (!strcmp(key, "count:sub_rejects")) return (double)c->sub_rejects;
   auto it = c->timers.ms.find(key);
   return it == c->timers.ms.end() ? 0.0 : it->second;
 }

@@ -52,7 +52,14 @@ static void scf_apply_huzinaga(nbd_ctx* c) {
   StageScope ts(c->timers, c->stream, "fock");
   const int n = c->nao;
   const long nn = (long)n * n;
-  gemm_nn(c, n, n, n, c->F.p, n, c->GS.p, n, c->FG.p, n, 1.0, 0.0, c->nspin, nn, nn, nn);
+  if (c->env_rank > 0) {
+    // gamma = V V^T has rank r << n: F gamma S = (F V)(V^T S), 4 n^2 r flop instead of 2 n^3  (r = 155 of 1376 at C4)
+    const int r = c->env_rank;
+    gemm_nt(c, n, r, n, c->F.p, n, c->envV.p, n, c->envW.p, r, 1.0, 0.0, c->nspin, nn, (long)r * n, (long)n * r);
+    gemm_nn(c, n, n, r, c->envW.p, r, c->envZ.p, n, c->FG.p, n, 1.0, 0.0, c->nspin, (long)n * r, (long)r * n, nn);
+  } else {
+    gemm_nn(c, n, n, n, c->F.p, n, c->GS.p, n, c->FG.p, n, 1.0, 0.0, c->nspin, nn, nn, nn);
+  }
   const double* FGv = nullptr;
   const double* W = nullptr;
   if (c->have_virt) {  // virtual-orbital projector (huzinaga_scf.py:82-88): FGv = F GSv, W = GSv^T FGv
@@ -253,6 +260,7 @@ extern "C" int nbd_scf_setup(nbd_ctx* c, int nspin, const int* nelec, const doub
     c->scf_ready = true;
     c->bench_ready = false;
     c->have_virt = false;
+    c->env_rank = 0;
     c->sub_valid = false;  // a tracked eigenvector block never survives a change of problem
     c->sub_bounds_valid = false;
     c->last_eig_full = true;
@@ -279,12 +287,49 @@ extern "C" int nbd_scf_set_virtual_projector(nbd_ctx* c, const double* dm_env_vi
   });
 }
 
+// Optional low-rank factor of the occupied environment density: dm_env_s = c_env_s c_env_s^T with c_env [nspin][nao][r]
+// (the localizer's c_enviro, nbed/localizers/system.py:33: dm_enviro = c_enviro c_enviro^T).  The projector product
+// F gamma S of get_huzinaga_operator (huzinaga_scf.py:77) then runs as two rank-r GEMMs.  The factor is checked against
+// the gamma S of nbd_scf_setup on the device; a factor that does not reproduce it is refused (NBD_ERR_ARG) and the
+// dense product stays in use.  Call after nbd_scf_setup.
+extern "C" int nbd_scf_set_env_orbitals(nbd_ctx* c, int r, const double* c_env) {
+  return guarded(c, [&] {
+    NBD_REQUIRE(c->scf_ready && c->projector == NBD_HUZINAGA, NBD_ERR_STATE, "nbd_scf_setup(projector = NBD_HUZINAGA) first");
+    NBD_REQUIRE(r >= 1 && c_env, NBD_ERR_ARG, "bad rank / pointer");
+    const int n = c->nao, ns = c->nspin;
+    const long nn = (long)n * n;
+    c->env_rank = 0;
+    if (2 * r > n) {  // no saving: keep the dense product
+      finish_call(c);
+      return;
+    }
+    c->envV.ensure((size_t)ns * r * n);
+    c->envZ.ensure((size_t)ns * r * n);
+    c->envW.ensure((size_t)ns * n * r);
+    h2d(c, c->envW.p, c_env, (size_t)ns * n * r);  // [ns][n][r]
+    {
+      dim3 g((r + 31) / 32, (n + 31) / 32, ns), b(32, 8);
+      transpose_kernel<<<g, b, 0, c->stream>>>(c->envW.p, c->envV.p, n, r);  // -> [ns][r][n]
+      LAUNCH_CHECK(c);
+    }
+    gemm_nn(c, r, n, n, c->envV.p, n, c->S.p, n, c->envZ.p, n, 1.0, 0.0, ns, (long)r * n, 0, (long)r * n);
+    // check: V (V^T S) == gamma S
+    gemm_tn(c, n, n, r, c->envV.p, n, c->envZ.p, n, c->T1.p, n, 1.0, 0.0, ns, (long)r * n, (long)r * n, nn);
+    double* out = c->red_out.ensure(64);
+    reduce_to(c, c->T1.p, c->GS.p, ns * nn, 1, n, out + 40);
+    reduce_to(c, c->GS.p, c->GS.p, ns * nn, 0, n, out + 41);
+    double h[2];
+    d2h(c, h, out + 40, 2);
+    NBD_CUDA(cudaStreamSynchronize(c->stream));
+    NBD_REQUIRE(h[0] <= 1e-20 * std::max(h[1], 1e-300), NBD_ERR_ARG,
+                "c_env does not factor dm_env: |c c^T S - dm S|_F / |dm S|_F = %.3e", std::sqrt(h[0] / std::max(h[1], 1e-300)));
+    c->env_rank = r;
+    c->bench_ready = false;
+    finish_call(c);
+  });
+}
+
 // ---- Huzinaga loop -----------------------------------------------------------------------------------
-struct HuzLoop {
-  int Ntot = 0;
-  std::vector<KGroup> groups;
-  bool orbitals_from_guess = true;
-};
 
 // initial guess of huzinaga_scf.py:139-148 (dm0 == null) or a dense user density
 static void huz_initial(nbd_ctx* c, const double* dm0, HuzLoop& L) {
@@ -353,14 +398,18 @@ extern "C" int nbd_huzinaga_scf(nbd_ctx* c, int max_cycle, double conv_tol, doub
     const long nn = (long)c->nao * c->nao;
     {
     StageScope ts_all(c->timers, c->stream, "scf_total");
+    const int eig_mode_in = c->eig_mode;
+    double eprev[2] = {0.0, 0.0}, e[2] = {0.0, 0.0}, nd = 0.0;
+    int conv = 0, cycles = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
     HuzLoop L;
     c->sub_valid = false;  // every SCF run starts from scratch (cold block / full diagonalisation / the caller's density)
     c->sub_bounds_valid = false;
     c->last_eig_full = true;
     huz_initial(c, dm0, L);
     c->diis.init(6, c->nspin * nn, false);
-    double eprev[2] = {0.0, 0.0}, e[2] = {0.0, 0.0}, nd = 0.0;
-    int conv = 0, cycles = 0;
+    eprev[0] = eprev[1] = e[0] = e[1] = nd = 0.0;
+    conv = cycles = 0;
     for (int i = 0; i < max_cycle; ++i) {
       StageScope ts(c->timers, c->stream, "iter_total");
       huz_iteration(c, i, use_diis != 0, L, e, &nd);
@@ -379,8 +428,33 @@ extern "C" int nbd_huzinaga_scf(nbd_ctx* c, int max_cycle, double conv_tol, doub
       eprev[0] = e[0];
       eprev[1] = e[1];
     }
-    scf_complete_spectrum(c);  // full (C, eps) of the last Fock matrix for the returned values
+    // Full (C, eps) of the last Fock matrix for the returned values.  It also audits the tracked block: a small
+    // residual proves an invariant subspace, not that it is the LOWEST one, so the Ritz values of the occupied
+    // orbitals must equal the nocc lowest eigenvalues of the complete spectrum.  If they do not (a missed or crossed
+    // level), the whole SCF is redone with the library eigensolver in every cycle.
+    const bool tracked = !c->last_eig_full;
+    double theta[2][32];
+    memcpy(theta, c->sub_theta, sizeof theta);
+    scf_complete_spectrum(c);
     check_devinfo(c, c->nspin, "Fock eigendecomposition");
+    if (tracked) {
+      double worst = 0.0;
+      std::vector<double> w(32);
+      for (int s = 0; s < c->nspin; ++s) {
+        const int o = std::min(scf_nocc(c, s), 32);
+        d2h(c, w.data(), c->evals.p + (long)s * c->nao, o);
+        NBD_CUDA(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < o; ++k) worst = std::max(worst, std::fabs(w[k] - theta[s][k]) / std::max(1.0, std::fabs(w[k])));
+      }
+      if (worst > 1e-8) {
+        ++c->sub_rejects;
+        c->eig_mode = 0;
+        continue;
+      }
+    }
+    break;
+    }  // attempt
+    c->eig_mode = eig_mode_in;
     scf_export(c, mo_coeff, mo_energy, dm, huz, c->Huz.p);
     if (result) {
       result->converged = conv;
@@ -397,17 +471,15 @@ extern "C" int nbd_huzinaga_scf(nbd_ctx* c, int max_cycle, double conv_tol, doub
 }
 
 // ---- benchmark stepper: the same loop body, one call per iteration --------------------------------------
-static HuzLoop g_bench_loop;  // per process (one context per process and GPU)
-
 extern "C" int nbd_scf_bench_init(nbd_ctx* c) {
   return guarded(c, [&] {
     c->timers.reset();
     NBD_REQUIRE(c->scf_ready && c->projector == NBD_HUZINAGA, NBD_ERR_STATE, "nbd_scf_setup(projector = NBD_HUZINAGA) first");
     const long nn = (long)c->nao * c->nao;
-    g_bench_loop = HuzLoop();
+    c->bench_loop = HuzLoop();
     {
       StageScope ts(c->timers, c->stream, "iter_total");
-      huz_initial(c, nullptr, g_bench_loop);
+      huz_initial(c, nullptr, c->bench_loop);
       c->diis.init(6, c->nspin * nn, false);
     }
     c->bench_ready = true;
@@ -422,7 +494,7 @@ extern "C" int nbd_scf_bench_iteration(nbd_ctx* c, int iter, double* energy2, do
     double e[2] = {0, 0}, nd = 0;
     {
       StageScope ts(c->timers, c->stream, "iter_total");
-      huz_iteration(c, iter, true, g_bench_loop, e, &nd);
+      huz_iteration(c, iter, true, c->bench_loop, e, &nd);
     }
     if (energy2) {
       energy2[0] = e[0];

@@ -15,10 +15,11 @@ All arithmetic runs on the GPU through ``nbed_b200.backend.B200Context``; there 
 from __future__ import annotations
 
 import copy as _copy
+import warnings
 
 import numpy as np
 
-from .backend import NBD_HUZINAGA, NBD_MU_SHIFT, B200Context
+from .backend import NBD_HUZINAGA, NBD_MU_SHIFT, B200Context, NbdError
 
 
 class TaggedArray(np.ndarray):
@@ -131,6 +132,38 @@ class _B200SCF:
             vhf = self.get_veff(dm=dm)
         return np.asarray(h1e) + vhf
 
+    def kernel(self, dm0=None, **kwargs):
+        """``pyscf.scf.hf.SCF.kernel``: the SCF loop of pyscf/scf/hf.py:kernel (CDIIS from cycle 1, generalised
+        eigensolve, conv_tol / sqrt(conv_tol) gradient test, one extra cycle after convergence) on the GPU, with whatever
+        ``get_hcore`` currently returns - so the reference's mu-shift sequence "patch get_hcore, call kernel()"
+        (nbed/driver.py:529-533) binds without an edit.  Returns ``e_tot`` and sets ``mo_coeff / mo_energy / mo_occ /
+        e_tot / converged`` like PySCF.
+
+        ``dm0 = None``: PySCF would build its 'minao' guess from atomic basis data, which lies outside the hot path (no
+        basis objects here); the core-Hamiltonian guess (PySCF's ``init_guess = '1e'``) is used instead, so the
+        converged result agrees with the reference to the convergence threshold but the iterates differ.  Pass the
+        reference's ``dm0`` for iterate-level parity."""
+        if not self.unrestricted:
+            raise NotImplementedError("kernel() is spin-resolved here (the reference's drivers build UHF/UKS objects)")
+        n = self.ctx.nao
+        h = np.asarray(self.get_hcore(), dtype=np.float64)
+        if dm0 is None:
+            import scipy.linalg
+
+            hs = h if h.ndim == 3 else np.array([h, h])
+            dm0 = []
+            for s in range(2):
+                _, c = scipy.linalg.eigh(hs[s], self._s)
+                dm0.append(c[:, : self.nelec[s]] @ c[:, : self.nelec[s]].T)
+            dm0 = np.array(dm0)
+        zero = np.zeros((2, n, n))
+        self.ctx.scf_setup(self.nelec, self._s, h, zero, zero, NBD_MU_SHIFT, 0.0)
+        c, e, occ, dm, vhf, info = self.ctx.mu_scf(self.max_cycle, self.conv_tol, self.energy_nuc(), dm0)
+        self.mo_coeff, self.mo_energy, self.mo_occ = c, e, occ
+        self.e_tot, self.converged = info["e_tot"], info["converged"]
+        self.scf_info = info
+        return self.e_tot
+
 
 class B200UHF(_B200SCF):
     unrestricted = True
@@ -221,6 +254,15 @@ def huzinaga_scf(scf_method, embedding_potential, dm_environment_occupied, dm_en
         raise ValueError("embedding_potential / dm_environment_occupied rank does not match the SCF object")
     ctx = scf_method.ctx
     ctx.scf_setup(scf_method.nelec, scf_method.get_ovlp(), scf_method.get_hcore(), v, g, NBD_HUZINAGA)
+    # dm_enviro of a LocalizedSystem carries the orbital block it was built from (dm = c c^T): low-rank projector
+    factor = getattr(dm_environment_occupied, "factor", None)
+    if factor is not None and np.shape(factor)[:-1] == g.shape[:-1]:
+        try:
+            ctx.scf_set_env_orbitals(factor)
+        except NbdError as err:  # a stale tag (array modified after tagging): keep the dense product
+            if err.code != -2:
+                raise
+            warnings.warn(f"ignoring dm_environment_occupied.factor: {err}")
     if dm_environment_virtual is not None:  # :133-134 (the PAO virtual projector)
         gv = np.asarray(dm_environment_virtual, dtype=np.float64)
         if gv.shape != g.shape:
@@ -274,11 +316,15 @@ def mu_embed(localized_scf, embedding_potential, dm_enviro, mu_level_shift: floa
     return localized_scf, v_emb
 
 
-# ---- nbed/driver.py:540-632 (NbedDriver._huzinaga_embed, without the PAO orbital reshuffling of :604-619) --------
-def huzinaga_embed(active_scf, embedding_potential, dm_enviro, dm_environment_virtual=None, dmat_initial_guess=None):
+# ---- nbed/driver.py:540-632 (NbedDriver._huzinaga_embed) ---------------------------------------------------------
+def huzinaga_embed(active_scf, embedding_potential, dm_enviro, dm_environment_virtual=None, dmat_initial_guess=None,
+                   localized_system=None):
     """Runs ``huzinaga_scf`` and writes the result onto the SCF object the way the driver does: patched ``get_hcore``
     (:595-597), ``mo_occ / mo_coeff / mo_energy`` (:602-622), ``e_tot = energy_tot(dm)`` (:627, one more J/K build on
-    the device) and ``converged``.  Returns ``(active_scf, v_emb)`` with ``v_emb = huzinaga_op + embedding_potential``."""
+    the device) and ``converged``.  Returns ``(active_scf, v_emb)`` with ``v_emb = huzinaga_op + embedding_potential``.
+
+    ``localized_system`` (optional ``LocalizedSystem``): when it carries ``c_loc_virt`` the embedded virtuals are
+    overwritten exactly as the reference does at :604-619 - including its slicing of the *leading* axis."""
     c, e, dm, huz, conv = huzinaga_scf(active_scf, embedding_potential, dm_enviro,
                                        dm_environment_virtual=dm_environment_virtual, dm_conv_tol=1e-6,
                                        dm_initial_guess=dmat_initial_guess)
@@ -286,7 +332,13 @@ def huzinaga_embed(active_scf, embedding_potential, dm_enviro, dm_environment_vi
     v_emb = huz + np.asarray(embedding_potential)
     active_scf.get_hcore = lambda *args: hcore_std + v_emb
     active_scf.mo_occ = active_scf.get_occ(e, c)
-    active_scf.mo_coeff = c
+    if localized_system is not None and localized_system.c_loc_virt is not None:  # :604-619
+        occ_any = np.sum(active_scf.mo_occ, axis=0)
+        active_scf.mo_coeff = np.concatenate(
+            (c[..., occ_any > 0], c[..., occ_any == 0][: localized_system.c_loc_virt.shape[-1]]), axis=2)
+        active_scf.mo_occ = active_scf.mo_occ[: active_scf.mo_coeff.shape[-1]]
+    else:
+        active_scf.mo_coeff = c
     active_scf.mo_energy = e
     active_scf.e_tot = active_scf.energy_tot(dm=dm)
     active_scf.converged = conv

@@ -11,8 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_bench_line_contract():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "C3", "--steps", "6", "--warmup", "3",
-                          "--cpu-sample-rows", "16"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "C3", "--steps", "6", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
@@ -31,3 +31,5 @@ def test_bench_line_contract():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert d["gpu_launches"] > 0 and "workload" in d["config"] and "model" not in d["config"]
     assert d["ao2mo"]["gbs"] > 0 and d["hamiltonian_build"]["wall_ms"] > 0
+    assert len(d["checksum"]["energy_last_step"]) == 2 and "FULL iterations" in d["cpu_baseline"]["sample"]
+    assert {"n", "naux", "nocc_per_spin", "n_env", "sharding"} <= set(d["config"])
