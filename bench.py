@@ -301,7 +301,7 @@ def run_b200(args):
         e, nd = ctx.scf_bench_iteration(it)
         log(f"warm-up iteration {it}: {ctx.timer_ms('iter_total'):.2f} ms E={e} |dD|={nd:.3e} {ctx.timers()}")
         it += 1
-    stage_keys = ("jk_x", "jk_rho", "jk_k", "jk_j", "jk_total", "allreduce", "fock", "diis", "orth", "eigh", "eig_sub",
+    stage_keys = ("jk_x", "jk_rho", "jk_k", "jk_j", "jk_total", "allreduce", "fock", "diis", "orth", "orth_gather", "eigh", "eig_sub",
                   "eig_bcast", "density", "energy", "iter_total")
     stages = {k: 0.0 for k in stage_keys}
     # The timed region runs embedded SCFs from the reference's core-Hamiltonian guess (huzinaga_scf.py:139-148),

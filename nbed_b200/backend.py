@@ -10,7 +10,7 @@ from ._lib import NBD_HUZINAGA, NBD_MU_SHIFT, NbdError, ScfResult, f64, pinned_e
 
 TIMER_KEYS = (
     "jk_x", "jk_rho", "jk_j", "jk_k", "jk_total", "allreduce", "fock", "diis", "orth", "eigh", "density", "energy",
-    "eig_sub", "eig_bcast", "iter_total", "scf_total", "ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm", "ao2mo_total", "spinorb",
+    "eig_sub", "eig_bcast", "orth_gather", "iter_total", "scf_total", "ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm", "ao2mo_total", "spinorb",
 )
 
 

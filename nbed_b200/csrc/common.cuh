@@ -75,6 +75,29 @@ __device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, uint
       : "memory");
 }
 
+// ---- thread-block clusters: barrier + distributed shared memory -----------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster; release / acquire at cluster scope (orders shared-memory writes before
+// remote reads) - without the GPU-scope fence and L1 invalidate that cooperative_groups' cluster.sync() adds
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ double dsmem_ld(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---- cp.async (LDGSTS) 8-byte with zero fill ----------------------------------------------------
 __device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid) {
   int sz = valid ? 8 : 0;

@@ -33,6 +33,7 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -57,7 +58,8 @@ struct NcclApi {
     Broadcast = (decltype(Broadcast))dlsym(lib, "ncclBroadcast");
     GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
     GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
-    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString || !Broadcast || !GroupStart || !GroupEnd) {
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+    if (!AllGather || !GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString || !Broadcast || !GroupStart || !GroupEnd) {
       why = "libnccl is missing required symbols";
       return false;
     }
@@ -126,6 +128,7 @@ struct nbd_ctx {
   int overlap = 1;
   int eig_threads = 1;  // second spin's full eigensolve issued from a helper thread on the side stream
   int dist_eig = 1;
+  int dist_orth = 1;  // multi-rank: every rank forms its row block of F' = X F X, one all-gather assembles it
   int gemm_tile = 0;      // tuning: force the GEMM tile size (0 = heuristic)
   int jpass_variant = 0;  // 0: TMA-fed persistent pass 2, 1: LDG streaming pass 2
   int panel_stages = 0;  // tuning: cap on the ring depth of the panel kernel (0 = as many as fit)
@@ -166,7 +169,7 @@ struct nbd_ctx {
   int nelec[2] = {0, 0};
   double mu = 0.0;
   DBuf<double> S, Xh, hcore, heff, GS, GSv, F, Huz, vhf, FG, T1, T2, Ct, D, Dold, evals, eigwork, eigwork2, red_part, red_out,
-      Corth, Ssave, dm0f;
+      Corth, Ssave, dm0f, Fpad;
   DBuf<int> devinfo;
   DiisState diis;
   // subspace (Chebyshev-filtered) tracking of the occupied block between full eigensolves
@@ -180,6 +183,7 @@ struct nbd_ctx {
   DBuf<double> sV, sY, sZ, sW, sAV, sPart, sG, sGpart, sM, sTheta, sRpart, sBound, sFprev, sLz;
   // spectral bounds of the filter: 0 = Gershgorin every cycle; 1 = Lanczos once, then widened by ||F'_k - F'_{k-1}||_F
   int sub_bound_mode = 1;
+  int sub_apply_variant = 0;  // 0: cluster split-K block product (4-CTA clusters, DSMEM reduction); 1: one CTA per 16 rows
   int sub_cold = 1;  // 1: the initial guess starts the block from pseudo-random vectors (no library eigensolve)
   bool sub_bounds_valid = false, sub_is_cold = false;
   double sub_up[2] = {0, 0}, sub_low[2] = {0, 0}, sub_up_ref[2] = {0, 0}, sub_low_ref[2] = {0, 0};
@@ -834,6 +838,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "overlap") c->overlap = (int)value;
   else if (k == "eig_threads") c->eig_threads = (int)value;
   else if (k == "dist_eig") c->dist_eig = (int)value;
+  else if (k == "dist_orth") c->dist_orth = (int)value;
   else if (k == "panel_stages") c->panel_stages = (int)value;
   else if (k == "panel_hybrid") c->panel_hybrid = (int)value;
   else if (k == "panel_warps") {
@@ -852,6 +857,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "eig_mode") { c->eig_mode = (int)value; c->sub_valid = false; }
   else if (k == "sub_bound") { c->sub_bound_mode = (int)value; c->sub_bounds_valid = false; }
   else if (k == "sub_cold") c->sub_cold = (int)value;
+  else if (k == "sub_apply_variant") c->sub_apply_variant = (int)value;
   else if (k == "sub_min_nao") { c->sub_min_nao = (int)value; c->sub_valid = false; }
   else return NBD_ERR_ARG;
   return NBD_OK;

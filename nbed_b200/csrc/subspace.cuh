@@ -145,6 +145,145 @@ __global__ void __launch_bounds__(128) sub_apply_kernel(SubApplyArgs a) {
   }
 }
 
+// ---- cluster split-K variant (default) -----------------------------------------------------------------------
+// The kernel above runs 86 x 2 CTAs that each walk the whole contraction index: it is latency-bound (17 us per block
+// product for 45 MB of L2 reads).  Here a CTA owns 32 rows (half the re-reads of Y) and a QUARTER of the contraction
+// index; the four CTAs of a thread-block cluster hold the four partial 32 x KB tiles in their shared memory and the
+// cluster's rank-0 CTA sums them over DSMEM in rank order (deterministic) and applies the epilogue.  4x the CTAs in
+// flight, a quarter of the serial chunk chain per CTA, no extra launch and no global-memory round trip.
+constexpr int SUB2_ROWS = 32;
+constexpr int SUB2_JCHUNK = 32;
+constexpr int SUB2_STAGES = 4;
+constexpr int SUB2_KS = 4;  // cluster size = split of the contraction index
+
+template <int KB>
+constexpr int sub_apply2_smem_bytes() {
+  // ring of stages, reused for the 4 per-warp partial tiles [4][32][KB]; the CTA's summed tile [32][KB] lives behind it
+  constexpr int ring = SUB2_STAGES * (SUB2_ROWS * (SUB2_JCHUNK + 4) + SUB2_JCHUNK * (KB + 4)) * 8;
+  constexpr int red = 4 * SUB2_ROWS * KB * 8;
+  return (ring > red ? ring : red) + SUB2_ROWS * KB * 8;
+}
+
+template <int KB>
+__global__ void __launch_bounds__(128) sub_apply2_kernel(SubApplyArgs a) {
+  constexpr int A_LD = SUB2_JCHUNK + 4, Y_LD = KB + 4, NI = KB / 8, MI = SUB2_ROWS / 8;
+  constexpr int A_ST = SUB2_ROWS * A_LD, Y_ST = SUB2_JCHUNK * Y_LD;
+  constexpr int RING = SUB2_STAGES * (A_ST + Y_ST), RED = 4 * SUB2_ROWS * KB;
+  extern __shared__ __align__(16) double sub_smem[];
+  double* As = sub_smem;
+  double* Ys = sub_smem + SUB2_STAGES * A_ST;
+  double* cta_tile = sub_smem + (RING > RED ? RING : RED);  // [32][KB], read by the cluster's rank-0 CTA
+  const int ks = (int)cluster_ctarank();  // which quarter of the contraction index
+  const int rb = blockIdx.x, b = blockIdx.z;
+  const int n = a.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const double* A = a.A + (long)b * n * n;
+  const double* Y = a.Y + (long)b * n * KB;
+  const int nchunk = (n + SUB2_JCHUNK - 1) / SUB2_JCHUNK;
+  const int ch0 = nchunk * ks / SUB2_KS, ch1 = nchunk * (ks + 1) / SUB2_KS;
+  const bool vec = (n & 1) == 0;  // rows of A start 16-byte aligned
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  auto load = [&](int ch, int buf) {
+    const int j0 = ch * SUB2_JCHUNK;
+    double* as = As + buf * A_ST;
+    double* ys = Ys + buf * Y_ST;
+    if (vec) {
+#pragma unroll
+      for (int q = 0; q < SUB2_ROWS * SUB2_JCHUNK / 2 / 128; ++q) {
+        const int e = tid + 128 * q;
+        const int r = e / (SUB2_JCHUNK / 2), j = 2 * (e % (SUB2_JCHUNK / 2));
+        const int gi = rb * SUB2_ROWS + r, gj = j0 + j;
+        const bool ok = gi < n && gj < n;
+        cp_async16(as + r * A_LD + j, ok ? A + (long)gi * n + gj : A, ok);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < SUB2_ROWS * SUB2_JCHUNK / 128; ++q) {
+        const int e = tid + 128 * q;
+        const int r = e / SUB2_JCHUNK, j = e % SUB2_JCHUNK;
+        const int gi = rb * SUB2_ROWS + r, gj = j0 + j;
+        const bool ok = gi < n && gj < n;
+        cp_async8(as + r * A_LD + j, ok ? A + (long)gi * n + gj : A, ok);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < SUB2_JCHUNK * KB / 2 / 128; ++q) {
+      const int e = tid + 128 * q;
+      const int j = e / (KB / 2), c2 = 2 * (e % (KB / 2));
+      const bool ok = j0 + j < n;
+      cp_async16(ys + j * Y_LD + c2, ok ? Y + (long)(j0 + j) * KB + c2 : Y, ok);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < SUB2_STAGES - 1; ++s) {
+    if (ch0 + s < ch1) load(ch0 + s, s);
+    cp_async_commit();
+  }
+  for (int ch = ch0; ch < ch1; ++ch) {
+    cp_async_wait<SUB2_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nx = ch + SUB2_STAGES - 1;
+      if (nx < ch1) load(nx, (nx - ch0) % SUB2_STAGES);
+      cp_async_commit();
+    }
+    const int buf = (ch - ch0) % SUB2_STAGES;
+    // warp w takes contraction indices [8 w, 8 w + 8) of the chunk (two k4 steps)
+    const double* as = As + buf * A_ST + gq * A_LD + 8 * warp + tq;
+    const double* ys = Ys + buf * Y_ST + (8 * warp + tq) * Y_LD + gq;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; k4 += 4) {
+      double af[MI], bf[NI];
+#pragma unroll
+      for (int i = 0; i < MI; ++i) af[i] = as[8 * i * A_LD + k4];
+#pragma unroll
+      for (int j = 0; j < NI; ++j) bf[j] = ys[k4 * Y_LD + 8 * j];
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) dmma(acc[i][j], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // the four warps' partial tiles -> this CTA's tile (fixed order)
+  double* red = sub_smem;  // [4][32][KB]
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      double* p = red + ((warp * SUB2_ROWS) + 8 * i + gq) * KB + 8 * j + 2 * tq;
+      p[0] = acc[i][j][0];
+      p[1] = acc[i][j][1];
+    }
+  __syncthreads();
+  for (int e = tid; e < SUB2_ROWS * KB; e += 128)
+    cta_tile[e] = ((red[e] + red[SUB2_ROWS * KB + e]) + red[2 * SUB2_ROWS * KB + e]) + red[3 * SUB2_ROWS * KB + e];
+  cluster_sync_all();  // all four partial tiles are in place (release / acquire at cluster scope)
+  if (ks == 0) {
+    const uint32_t t0 = smem_u32(cta_tile);
+    const uint32_t t1 = dsmem_addr(t0, 1), t2 = dsmem_addr(t0, 2), t3 = dsmem_addr(t0, 3);
+    const double alpha = b == 0 ? a.alpha[0] : a.alpha[1], shift = b == 0 ? a.shift[0] : a.shift[1],
+                 beta = b == 0 ? a.beta[0] : a.beta[1];
+    const double* Z = a.Z ? a.Z + (long)b * n * KB : nullptr;
+    double* out = a.out + (long)b * n * KB;
+    for (int e = tid; e < SUB2_ROWS * KB; e += 128) {
+      const int gi = rb * SUB2_ROWS + e / KB;
+      if (gi >= n) continue;
+      const double s = ((cta_tile[e] + dsmem_ld(t1 + 8u * e)) + dsmem_ld(t2 + 8u * e)) + dsmem_ld(t3 + 8u * e);
+      const long o = (long)gi * KB + e % KB;
+      double v = alpha * (s - shift * Y[o]);
+      if (Z) v -= beta * Z[o];
+      out[o] = v;
+    }
+  }
+  cluster_sync_all();  // the peers' shared memory stays alive until rank 0 has read it
+}
+
 // G[b][0] = Y^T Y, G[b][1] = Y^T W  (KB x KB each), rows split over gridDim.x CTAs, deterministic final sum.
 template <int KB>
 __global__ void __launch_bounds__(256) sub_gram_kernel(const double* __restrict__ Yall, const double* __restrict__ Wall,

@@ -187,6 +187,29 @@ static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double
   for (int b = 0; b < 2; ++b) {
     a.alpha[b] = alpha[b]; a.shift[b] = shift[b]; a.beta[b] = beta[b];
   }
+  if (c->sub_apply_variant == 0) {
+    // cluster split-K kernel: 32 rows per CTA, 4 CTAs of a cluster share the contraction index, DSMEM reduction
+    constexpr int smem2 = sub_apply2_smem_bytes<KB>();
+    static unsigned long long configured2 = 0;
+    if (first_use_on_current_device(configured2))
+      NBD_CUDA(cudaFuncSetAttribute(sub_apply2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((n + SUB2_ROWS - 1) / SUB2_ROWS, SUB2_KS, c->nspin);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem2;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = SUB2_KS;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NBD_CUDA(cudaLaunchKernelEx(&cfg, sub_apply2_kernel<KB>, a));
+    LAUNCH_CHECK(c);
+    ++c->sub_applies;
+    return;
+  }
   dim3 g(nrb, 1, c->nspin);
   constexpr int smem = sub_apply_smem_bytes<KB>();
   static unsigned long long configured = 0;
