@@ -50,8 +50,7 @@ int nbd_set_option(nbd_ctx* ctx, const char* key, long value);
  * "overlap" (0 = pass 2 behind the K Gram, 1 = side stream, 3 = same stream with programmatic dependent launch),
  * "sub_bound" (1 = Lanczos + ||dF||_F spectral bounds, 0 = row sums), "sub_cold" (1 = initial guess by cold-start
  * subspace iteration, 0 = cuSOLVER), "dist_eig", "panel_stages", "panel_hybrid" (1 = 9-10 column slices run 8 columns on DMMA + 1-2 on the
- * FMA pipe, 0 = padded to 16 DMMA columns), "panel_warps" (8; 16 = EXPERIMENTAL 16-consumer-warp panel kernel and 16 x 16 super-block
- * storage order, must be set before nbd_cderi_alloc, not yet validated on a GPU), "x_budget_mb", "timers". */
+ * FMA pipe, 0 = padded to 16 DMMA columns), "x_budget_mb", "timers". */
 double nbd_timer_ms(nbd_ctx* ctx, const char* key);
 /* Number of kernels launched by this library since the context was created (bench "gpu_launches"). */
 long nbd_launch_count(nbd_ctx* ctx);

@@ -17,7 +17,6 @@
 #include "gemm.cuh"
 #include "host_util.cuh"
 #include "jk.cuh"
-#include "jk_panel16.cuh"
 #include "scf_kernels.cuh"
 #include "subspace.cuh"
 
@@ -132,7 +131,6 @@ struct nbd_ctx {
   int gemm_tile = 0;      // tuning: force the GEMM tile size (0 = heuristic)
   int jpass_variant = 0;  // 0: TMA-fed persistent pass 2, 1: LDG streaming pass 2
   int panel_stages = 0;  // tuning: cap on the ring depth of the panel kernel (0 = as many as fit)
-  int panel_warps = 8;   // EXPERIMENTAL: 16 = 16-consumer-warp panel kernel + 16 x 16 super-block tile order (set before nbd_cderi_alloc)
   int panel_hybrid = 1;  // 9-10 trailing orbital columns: 8 on DMMA + 1-2 on the FMA pipe (0 = pad to 16 DMMA columns)
   std::string err;
   long launches = 0;
@@ -175,7 +173,7 @@ struct nbd_ctx {
   // subspace (Chebyshev-filtered) tracking of the occupied block between full eigensolves
   int eig_mode = 1;  // 0: cuSOLVER every cycle; 1: filtered subspace iteration when eligible (cuSOLVER first / last / fallback)
   bool sub_valid = false;
-  int sub_min_nao = 256;  // below this the library eigensolver is cheaper than tracking a 16/32-vector block
+  int sub_min_nao = 128;  // below this the library eigensolver is cheaper than tracking a 16/32-vector block (C3, n = 174: 538 vs 254 iterations/s, profiles/bench_r02c_C3_*.json)
   bool last_eig_full = true;
   int sub_kb = 0;
   long sub_applies = 0, sub_fallbacks = 0, sub_outer = 0, sub_lanczos = 0, sub_cold_starts = 0;
@@ -263,14 +261,6 @@ static void launch_symm_panel(nbd_ctx* c, const XArgs& a, int grid, size_t smem)
   LAUNCH_CHECK(c);
 }
 
-template <int NSLOT, int NF>
-static void launch_symm_panel16(nbd_ctx* c, const XArgs& a, int grid, size_t smem) {
-  auto kern = symm_panel16_kernel<NSLOT, NF>;
-  NBD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, XK16_THREADS, smem, c->stream>>>(a);
-  LAUNCH_CHECK(c);
-}
-
 // Group-major layout of the half-transformed tensor for a chunk of np aux rows: the columns of group g
 // ([c0, c1), width w) form a dense [np * w][n_ld] matrix (row = (P, i)), so the Gram / second half-transform
 // GEMMs see a plain strided operand.  Returns the offset of each group; fills the device tables.
@@ -323,11 +313,9 @@ static void half_transform_cols(nbd_ctx* c, int p0, int np, const double* d_orb,
   NBD_REQUIRE(smem_for(ncolmax, 2, zrow) <= c->smem_optin, NBD_ERR_UNSUPPORTED, "nao = %d: orbital slice does not fit shared memory", c->nao);
   int stages = c->panel_stages > 0 ? std::min(16, std::max(2, c->panel_stages)) : 16;
   while (stages > 2 && smem_for(ncolmax, stages, zrow) > c->smem_optin) --stages;
-  // EXPERIMENTAL 16-warp kernel: hybrid slices only, up to 3 accumulator slots per warp (n <= 1536)
-  const bool wide = nf > 0 && c->panel_warps == 16 && (c->nb + 15) / 16 <= 3;
-  PlanDev& pd = c->plans[wide ? 100 + stages : stages];  // per-warp task lists for this (matrix size, ring depth, warp count); cleared on re-allocation
+  PlanDev& pd = c->plans[stages];  // per-warp task lists for this (matrix size, ring depth); cleared on re-allocation
   if (pd.events.p == nullptr) {
-    const PanelPlan plan = wide ? build_panel_plan_w(c->nb, stages, c->seq, 16) : build_panel_plan(c->nb, stages, c->seq);
+    const PanelPlan plan = build_panel_plan(c->nb, stages, c->seq);
     NBD_REQUIRE(plan.S == stages, NBD_ERR_STATE, "panel task lists failed their self-check (nb = %d, stages = %d)", c->nb, stages);
     uint32_t* de = pd.events.ensure(std::max<size_t>(1, plan.events.size()));
     int* db = pd.begin.ensure(plan.begin.size());
@@ -360,18 +348,7 @@ static void half_transform_cols(nbd_ctx* c, int p0, int np, const double* d_orb,
   const size_t smem = smem_for(ncolmax, stages, zrow);
 #define NBD_XK(NS, NBB) launch_symm_panel<NS, NBB>(c, a, (int)grid, smem)
 #define NBD_XKF(NS, NFF) launch_symm_panel<NS, 1, NFF>(c, a, (int)grid, smem)
-  if (wide) {
-    const int ns16 = (c->nb + 15) / 16;
-    if (nf == 1) {
-      if (ns16 <= 1) launch_symm_panel16<1, 1>(c, a, (int)grid, smem);
-      else if (ns16 <= 2) launch_symm_panel16<2, 1>(c, a, (int)grid, smem);
-      else launch_symm_panel16<3, 1>(c, a, (int)grid, smem);
-    } else {
-      if (ns16 <= 1) launch_symm_panel16<1, 2>(c, a, (int)grid, smem);
-      else if (ns16 <= 2) launch_symm_panel16<2, 2>(c, a, (int)grid, smem);
-      else launch_symm_panel16<3, 2>(c, a, (int)grid, smem);
-    }
-  } else if (nf == 1) {
+  if (nf == 1) {
     if (nslot <= 1) NBD_XKF(1, 1);
     else if (nslot <= 2) NBD_XKF(2, 1);
     else if (nslot <= 4) NBD_XKF(4, 1);
@@ -841,17 +818,6 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "dist_orth") c->dist_orth = (int)value;
   else if (k == "panel_stages") c->panel_stages = (int)value;
   else if (k == "panel_hybrid") c->panel_hybrid = (int)value;
-  else if (k == "panel_warps") {
-    if (value != 8 && value != 16) {  // (no exception may cross the C ABI here: this function is not guarded)
-      c->err = "panel_warps must be 8 or 16";
-      return NBD_ERR_ARG;
-    }
-    if (c->Bt != nullptr && (int)value != c->panel_warps) {
-      c->err = "panel_warps fixes the storage order: set it before nbd_cderi_alloc";
-      return NBD_ERR_STATE;
-    }
-    c->panel_warps = (int)value;
-  }
   else if (k == "jpass_variant") c->jpass_variant = (int)value;
   else if (k == "gemm_tile") c->gemm_tile = (int)value;
   else if (k == "eig_mode") { c->eig_mode = (int)value; c->sub_valid = false; }
@@ -930,7 +896,7 @@ int nbd_cderi_alloc(nbd_ctx* c, int nao, int naux_local) {
     c->ntiles = c->nb * (c->nb + 1) / 2;
     c->npair = (long)nao * (nao + 1) / 2;
     c->naux = naux_local;
-    c->seq = c->panel_warps == 16 ? build_tile_sequence_w(c->nb, 16) : build_tile_sequence(c->nb);
+    c->seq = build_tile_sequence(c->nb);
     c->plans.clear();
     NBD_REQUIRE((int)c->seq.size() == c->ntiles, NBD_ERR_STATE, "tile sequence has %zu entries, expected %d", c->seq.size(), c->ntiles);
     c->inv.assign((size_t)c->nb * c->nb, -1);

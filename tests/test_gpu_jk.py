@@ -161,27 +161,3 @@ def test_jk_hybrid_panel_matches_padded_panel(ctx):
             ctx.set_option("panel_hybrid", 1)
         scale = max(1.0, np.abs(vk0).max(), np.abs(vj0).max())
         assert np.abs(vj1 - vj0).max() <= 1e-13 * scale and np.abs(vk1 - vk0).max() <= 1e-13 * scale
-
-
-@pytest.mark.skipif(os.environ.get("NBED_EXPERIMENTAL") != "1",
-                    reason="experimental 16-warp panel kernel: compiled and host-checked only (DESIGN.md section 8); "
-                           "set NBED_EXPERIMENTAL=1 to run it")
-@pytest.mark.parametrize("n,naux,nocc", [(100, 8, (5, 4)), (300, 7, (5, 5)), (520, 6, (13, 13)), (1376, 3, (5, 5))])
-def test_jk_experimental_16_warp_panel_kernel(n, naux, nocc):
-    """Option panel_warps = 16 (own context: the option fixes the storage order of the tensor)."""
-    from nbed_b200.backend import B200Context
-
-    c = B200Context(0)
-    try:
-        c.set_option("panel_warps", 16)
-        rng = np.random.default_rng(n)
-        b = _cderi(n, naux)
-        c.load_cderi(b)
-        assert np.array_equal(c.cderi_download(0, naux), b)
-        orbs = [rng.normal(size=(n, o)) / np.sqrt(n) for o in nocc]
-        vj, vk = c.jk_orbitals(orbs)
-        rj, rk = ps.df_get_jk_occ(b, orbs)
-        scale = max(1.0, np.abs(rj).max(), np.abs(rk).max())
-        assert np.abs(vj - rj).max() <= 1e-12 * scale and np.abs(vk - rk).max() <= 1e-12 * scale
-    finally:
-        c.close()

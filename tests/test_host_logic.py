@@ -160,13 +160,3 @@ def test_host_linear_algebra_of_the_scf_drivers(tmp_path):
     subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(exe), src], check=True, timeout=300)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "fails=0" in out.stdout, out.stdout[-800:]
-
-
-def test_panel16_lane_arithmetic_emulation(tmp_path):
-    """Experimental 16-warp panel kernel (option panel_warps = 16): host emulation of the FMA-column lane arithmetic -
-    fragment indexing, the reduce-scatter over the four tq lanes, the row each lane finally owns."""
-    exe = tmp_path / "panel16_emul"
-    src = os.path.join(ROOT, "tests", "cpp", "panel16_emul.cpp")
-    subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(exe), src], check=True, timeout=300)
-    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
-    assert out.returncode == 0 and "fails=0" in out.stdout, out.stdout[-800:]
