@@ -41,7 +41,7 @@ int nbd_set_option(nbd_ctx* ctx, const char* key, long value);
 /* Per-stage device timings (CUDA events) of the last call, in milliseconds.
  * keys: "jk_x" (pass 1), "jk_rho", "jk_j" (pass 2), "jk_k" (Gram), "jk_total", "allreduce", "fock", "diis", "orth",
  *       "eigh" (cuSOLVER), "eig_sub" (filtered subspace iteration), "eig_bcast", "density", "energy", "iter_total",
- *       "scf_total", "ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm", "ao2mo_total", "spinorb", "build_total".
+ *       "scf_total", "ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm", "ao2mo_total", "spinorb", "build_total", "int3c2e", "cholesky".
  * Cumulative counters since context creation: "count:sub_applies", "count:sub_outer", "count:sub_fallbacks",
  * "count:sub_cold_starts", "count:sub_lanczos", "count:sub_rejects" (SCF runs redone with cuSOLVER because the tracked
  * block's Ritz values disagreed with the final full spectrum).
@@ -78,6 +78,24 @@ int nbd_cderi_upload(nbd_ctx* ctx, const double* cderi_rows, int row0, int nrows
 int nbd_cderi_synth(nbd_ctx* ctx, unsigned long long seed, double scale, int global_row0);
 /* Read back local rows in packed-lower layout (round-trip test of the layout transform). */
 int nbd_cderi_download(nbd_ctx* ctx, double* cderi_rows, int row0, int nrows);
+
+/* Density-fitting integrals generated ON THE DEVICE from a libcint-format basis.
+ * Replaces: pyscf.df.incore.cholesky_eri(mol, auxbasis) - aux_e2(mol, auxmol, 'int3c2e', aosym='s2ij'),
+ * auxmol.intor('int2c2e'), Cholesky decoration - which mf.density_fit() runs through libcint once per geometry
+ * (J/K call sites: nbed/scf/huzinaga_scf.py:156, nbed/driver.py:533).  Not part of the timed loop.
+ * atm [natm][6], bas [nbas][8], env [nenv]: PySCF's mol._atm / _bas / _env of the concatenated mol + auxmol
+ * (gto.mole.conc_mol, as aux_e2 builds it): orbital shells [0, nbas_ao), auxiliary shells [nbas_ao, nbas); real
+ * spherical functions; coefficients as PySCF stores them (primitive and contraction normalisation folded in);
+ * orbital l <= 3, auxiliary l <= 4, general contractions (nctr > 1) accepted.
+ * nbd_int3c2e: undecorated (P|mu>=nu) [naux][nao(nao+1)/2] and (P|Q) [naux][naux] to host buffers (either may be NULL).
+ * nbd_cderi_from_basis: allocates the device tensor (nao from the basis) and fills aux rows
+ * [global_row0, global_row0 + naux_local) of cderi = L^-1 (P|mu nu), (P|Q) = L L^T; naux_local = -1: all rows.
+ * nbd_basis_dims: nao / naux of such a basis (no context needed). */
+int nbd_basis_dims(const int* bas, int nbas, int nbas_ao, int* nao, int* naux);
+int nbd_int3c2e(nbd_ctx* ctx, const int* atm, int natm, const int* bas, int nbas, const double* env, int nenv,
+                int nbas_ao, double* j3c, double* j2c);
+int nbd_cderi_from_basis(nbd_ctx* ctx, const int* atm, int natm, const int* bas, int nbas, const double* env, int nenv,
+                         int nbas_ao, int global_row0, int naux_local);
 
 /* ---- J/K --------------------------------------------------------------------------------------- */
 /* Replaces: pyscf.df.df_jk.get_jk occupied-orbital branch (reached from scf_method.get_veff / get_jk /

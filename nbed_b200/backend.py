@@ -107,6 +107,41 @@ class B200Context:
         if cderi.shape[0]:
             self.cderi_upload(cderi, 0)
 
+    # -- density-fitting integrals on the device (libcint-format basis of mol + auxmol) ---------------------
+    @staticmethod
+    def _basis_arrays(atm, bas, env):
+        atm = np.ascontiguousarray(atm, dtype=np.int32).reshape(-1, 6)
+        bas = np.ascontiguousarray(bas, dtype=np.int32).reshape(-1, 8)
+        return atm, bas, f64(env)
+
+    def basis_dims(self, bas, nbas_ao: int):
+        bas = np.ascontiguousarray(bas, dtype=np.int32).reshape(-1, 8)
+        nao, naux = C.c_int(), C.c_int()
+        rc = self._lib.nbd_basis_dims(ptr(bas), bas.shape[0], int(nbas_ao), C.cast(C.byref(nao), C.c_void_p),
+                                      C.cast(C.byref(naux), C.c_void_p))
+        if rc != 0:
+            raise NbdError(rc, "bad basis arrays")
+        return nao.value, naux.value
+
+    def int3c2e(self, atm, bas, env, nbas_ao: int):
+        """Undecorated (P|mu>=nu) [naux, nao(nao+1)/2] and (P|Q) [naux, naux] (aux_e2 'int3c2e' s2ij, 'int2c2e')."""
+        atm, bas, env = self._basis_arrays(atm, bas, env)
+        nao, naux = self.basis_dims(bas, nbas_ao)
+        j3c, j2c = np.empty((naux, nao * (nao + 1) // 2)), np.empty((naux, naux))
+        self._ck(self._lib.nbd_int3c2e(self._h, ptr(atm), atm.shape[0], ptr(bas), bas.shape[0], ptr(env), env.size,
+                                       int(nbas_ao), ptr(j3c), ptr(j2c)))
+        return j3c, j2c
+
+    def cderi_from_basis(self, atm, bas, env, nbas_ao: int, global_row0: int = 0, naux_local: int = -1):
+        """``mf.density_fit()``: Cholesky-decorated tensor generated on the device, rows [global_row0, +naux_local)."""
+        atm, bas, env = self._basis_arrays(atm, bas, env)
+        nao, naux = self.basis_dims(bas, nbas_ao)
+        self._ck(self._lib.nbd_cderi_from_basis(self._h, ptr(atm), atm.shape[0], ptr(bas), bas.shape[0], ptr(env), env.size,
+                                                int(nbas_ao), int(global_row0), int(naux_local)))
+        self.nao = nao
+        self.naux_local = naux - global_row0 if naux_local < 0 else int(naux_local)
+        return nao, naux
+
     # -- J/K -------------------------------------------------------------------------------------
     def jk_orbitals(self, orbs, signs=None, with_j=True, with_k=True):
         """orbs: list of (nao, ncol) scaled occupied-orbital blocks; returns (vj, vk) of shape (nset, nao, nao)."""

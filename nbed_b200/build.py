@@ -44,7 +44,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
         "-Xcompiler", "-fPIC", "-shared", "-I", _nccl_include(), "-I", os.path.join(HERE, "..", "include"),
         "-o", LIB,
-    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcusolver", "-ldl", "-Xlinker", "-rpath=" + cuda_lib]
+    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcusolver", "-lcublas", "-ldl", "-Xlinker", "-rpath=" + cuda_lib]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

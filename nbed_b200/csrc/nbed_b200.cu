@@ -98,6 +98,8 @@ struct DiisState {
   }
 };
 
+void nbd_destroy_blas(struct cublasContext* h);  // defined next to the cuBLAS include (integrals_host.cuh)
+
 struct PlanDev {
   DBuf<uint32_t> events;
   DBuf<int> begin;
@@ -118,6 +120,7 @@ struct nbd_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cusolverDnHandle_t solver = nullptr;
+  struct cublasContext* blas = nullptr;  // only for the one-time triangular solve of the Cholesky decoration (integrals_host.cuh)
   // side stream (+ its own cuSOLVER handle): runs the HBM-bound J pass next to the tensor-bound K Gram, and the
   // second spin's eigensolve next to the first
   cudaStream_t stream2 = nullptr;
@@ -792,6 +795,7 @@ int nbd_destroy(nbd_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   if (c->Bt) cudaFree(c->Bt);
   if (c->solver) cusolverDnDestroy(c->solver);
+  if (c->blas) nbd_destroy_blas(c->blas);
   if (c->solver2) cusolverDnDestroy(c->solver2);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -1117,3 +1121,4 @@ extern "C" int nbd_jk_dm(nbd_ctx* c, int nset, const double* dm, double* vj, dou
 #include "subspace_host.cuh"
 #include "scf_host.cuh"
 #include "ao2mo_host.cuh"
+#include "integrals_host.cuh"

@@ -133,3 +133,55 @@ def test_c_restatement_agrees_with_numpy_restatement():
     full = c_binding.unpack_tril(b, p.n)
     il = np.tril_indices(p.n)
     assert np.array_equal(full[:, il[0], il[1]], b) and np.array_equal(full, full.transpose(0, 2, 1))
+
+
+def test_gto_restatement_conventions_and_consistency():
+    """oracle/gto_restatement.py (what the device integral generator is checked against): libcint's c2s constants,
+    normalised contractions, d-type auxiliary functions against the older s/p generator's exact four-centre code
+    (a product of two Gaussians on one centre IS one Gaussian), and two- against three-centre integrals."""
+    from oracle import gaussian_integrals as gi
+    from oracle import gto_restatement as g
+
+    t2 = g.cart2sph(2)
+    assert abs(t2[0, 1] - 1.092548430592079070) < 1e-15 and abs(t2[2, 5] - 0.630783130505040012) < 1e-15
+    assert abs(t2[2, 0] + 0.315391565252520002) < 1e-15 and abs(t2[4, 0] - 0.546274215296039535) < 1e-15
+    t3 = g.cart2sph(3)
+    assert abs(t3[0, 1] - 1.770130769779930531) < 1e-14 and abs(t3[0, 6] + 0.590043589926643510) < 1e-14
+    assert abs(t3[1, 4] - 2.890611442640554055) < 1e-14
+    atoms = g.parse_xyz(open(os.path.join(os.path.dirname(__file__), "golden", "water.xyz")).read())
+    atm, bas, env = g.make_env(atoms, g.CCPVDZ)
+    ao = g.shells_from_env(atm, bas, env)
+    s, t, v = g.int1e_sph(ao, atoms)
+    assert g.nao_sph(ao) == 24 and np.abs(np.diag(s) - 1).max() < 1e-14 and np.linalg.eigvalsh(s).min() > 1e-3
+    assert abs(g.energy_nuc(atoms) - 9.285714221677825) < 1e-12  # tests/test_driver.py:56
+    # STO-3G: identical to the generator that reproduces the reference's golden energies
+    atm, bas, env = g.make_env(atoms, gi.STO3G)
+    sto = g.shells_from_env(atm, bas, env)
+    old = gi.integrals(atoms)
+    s1, t1, v1 = g.int1e_sph(sto, atoms)
+    assert np.abs(s1 - old["S"]).max() < 1e-13 and np.abs(t1 - old["T"]).max() < 1e-12 and np.abs(v1 - old["V"]).max() < 1e-12
+    # d auxiliary function = s(a) x d(b) product on one centre: three-centre integral == exact four-centre integral
+    a, b, o = 0.7, 1.3, atoms[0][1]
+    j3 = g.int3c2e_sph(sto, [(o, 2, np.array([a + b]), np.array([1.0]))])
+    fns = gi.build_basis(atoms)
+
+    class Prim:
+        def __init__(self, lmn, e):
+            self.center, self.lmn, self.exps, self.coefs = np.asarray(o, float), lmn, [e], np.array([1.0])
+
+    comps = g.cart_components(2)
+    cart = np.zeros((6, 7, 7))
+    keep = []
+    for k, lmn in enumerate(comps):
+        fs, fd = Prim((0, 0, 0), a), Prim(lmn, b)
+        keep += [fs, fd]
+        cache = {}
+        for i in range(7):
+            for j in range(i + 1):
+                cart[k, i, j] = cart[k, j, i] = gi._eri_contracted(fs, fd, fns[i], fns[j], cache)
+    assert np.abs(np.einsum("mk,kij->mij", t2, cart) - j3).max() < 1e-14
+    aux = [(o, 2, np.array([0.9]), np.array([1.0])), (atoms[1][1], 3, np.array([0.6]), np.array([1.0]))]
+    sa, sb = (o, 0, np.array([0.5]), np.array([1.0])), (o, 0, np.array([0.8]), np.array([1.0]))
+    j3s = g.int3c2e_sph([sa, sb], aux)[:, 0, 1]
+    j2s = g.int2c2e_sph(aux + [(o, 0, np.array([1.3]), np.array([1.0]))])[-1, :-1]
+    assert np.abs(j3s - j2s * 0.282094791773878143).max() < 1e-14
