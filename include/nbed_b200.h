@@ -41,7 +41,7 @@ int nbd_set_option(nbd_ctx* ctx, const char* key, long value);
 /* Per-stage device timings (CUDA events) of the last call, in milliseconds.
  * keys: "jk_x" (pass 1), "jk_rho", "jk_j" (pass 2), "jk_k" (Gram), "jk_total", "allreduce", "fock", "diis", "orth",
  *       "eigh" (cuSOLVER), "eig_sub" (filtered subspace iteration), "eig_bcast", "density", "energy", "iter_total",
- *       "scf_total", "ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm", "ao2mo_total", "spinorb", "build_total", "int3c2e", "cholesky".
+ *       "scf_total", "ao2mo_half", "ao2mo_l", "ao2mo_eri", "ao2mo_perm", "ao2mo_total", "spinorb", "build_total", "int3c2e", "cholesky", "xc_ao", "xc".
  * Cumulative counters since context creation: "count:sub_applies", "count:sub_outer", "count:sub_fallbacks",
  * "count:sub_cold_starts", "count:sub_lanczos", "count:sub_rejects" (SCF runs redone with cuSOLVER because the tracked
  * block's Ritz values disagreed with the final full spectrum).
@@ -96,6 +96,23 @@ int nbd_int3c2e(nbd_ctx* ctx, const int* atm, int natm, const int* bas, int nbas
                 int nbas_ao, double* j3c, double* j2c);
 int nbd_cderi_from_basis(nbd_ctx* ctx, const int* atm, int natm, const int* bas, int nbas, const double* env, int nenv,
                          int nbas_ao, int global_row0, int naux_local);
+
+/* ---- exchange-correlation (Kohn-Sham objects) ------------------------------------------------------ */
+/* Replaces, for UKS objects, what scf_method.get_veff reaches beyond J/K (nbed/scf/huzinaga_scf.py:55,156 with the
+ * objects of nbed/driver.py:289-313; calculate_ks_energy :36-62): pyscf.dft.numint.eval_ao + NumInt.nr_uks + libxc.
+ * The quadrature is an INPUT: coords [ngrid][3] (Bohr) and weights [ngrid] = PySCF's mf.grids.coords / weights.
+ * atm / bas / env: libcint arrays of the ORBITAL basis (all nbas shells), l <= 3.  xc_code: 1 = 'b3lyp' (libxc
+ * HYB_GGA_XC_B3LYP: 0.08 Slater + 0.72 B88 + 0.19 VWN_RPA + 0.81 LYP, 20 % exact exchange), 2 = Slater + VWN_RPA (LDA).
+ * AO values and gradients on the grid stay resident on the device.  After the 3-centre tensor exists. */
+int nbd_xc_setup(nbd_ctx* ctx, int xc_code, const int* atm, int natm, const int* bas, int nbas, const double* env,
+                 int nenv, int ngrid, const double* coords, const double* weights);
+/* NumInt.nr_uks: dm host [2][nao][nao] -> nelec[2], exc (grid integral of the energy density, without the
+ * exact-exchange part), vxc host [2][nao][nao].  Any output may be NULL. */
+int nbd_xc_nr_uks(nbd_ctx* ctx, const double* dm, double* nelec, double* exc, double* vxc);
+/* on = 1: nbd_huzinaga_scf / nbd_mu_scf treat the SCF object as UKS: get_veff = J - hyb K + V_xc, the Huzinaga loop
+ * uses calculate_ks_energy (ecoul + exc + tr[D (h + Huz + V)]); nbd_mu_scf keeps nbed's patched energy_elec unless
+ * option "ks_energy" = 1 (plain pyscf UKS.energy_elec: e1 + ecoul + exc).  Spin-resolved (nspin = 2) only. */
+int nbd_scf_set_xc(nbd_ctx* ctx, int on);
 
 /* ---- J/K --------------------------------------------------------------------------------------- */
 /* Replaces: pyscf.df.df_jk.get_jk occupied-orbital branch (reached from scf_method.get_veff / get_jk /

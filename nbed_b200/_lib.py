@@ -17,7 +17,7 @@ NBD_MU_SHIFT = 1
 EXPORTS = [
     "nbd_version", "nbd_create", "nbd_destroy", "nbd_last_error", "nbd_set_option", "nbd_timer_ms",
     "nbd_launch_count", "nbd_host_alloc", "nbd_host_free", "nbd_comm_unique_id", "nbd_comm_init", "nbd_cderi_alloc", "nbd_cderi_upload",
-    "nbd_cderi_synth", "nbd_cderi_download", "nbd_basis_dims", "nbd_int3c2e", "nbd_cderi_from_basis", "nbd_jk", "nbd_jk_dm", "nbd_scf_setup", "nbd_scf_set_virtual_projector", "nbd_scf_set_env_orbitals", "nbd_huzinaga_scf",
+    "nbd_cderi_synth", "nbd_cderi_download", "nbd_basis_dims", "nbd_int3c2e", "nbd_cderi_from_basis", "nbd_xc_setup", "nbd_xc_nr_uks", "nbd_scf_set_xc", "nbd_jk", "nbd_jk_dm", "nbd_scf_setup", "nbd_scf_set_virtual_projector", "nbd_scf_set_env_orbitals", "nbd_huzinaga_scf",
     "nbd_mu_scf", "nbd_scf_bench_init", "nbd_scf_bench_iteration", "nbd_ao2mo", "nbd_one_body",
     "nbd_spinorb_from_spatial", "nbd_build_hamiltonian",
 ]
@@ -72,6 +72,9 @@ def load() -> C.CDLL:
         "nbd_cderi_synth": (I, [P, C.c_ulonglong, D, I]),
         "nbd_cderi_download": (I, [P, P, I, I]),
         "nbd_basis_dims": (I, [P, I, I, P, P]),
+        "nbd_xc_setup": (I, [P, I, P, I, P, I, P, I, I, P, P]),
+        "nbd_xc_nr_uks": (I, [P, P, P, P, P]),
+        "nbd_scf_set_xc": (I, [P, I]),
         "nbd_int3c2e": (I, [P, P, I, P, I, P, I, I, P, P]),
         "nbd_cderi_from_basis": (I, [P, P, I, P, I, P, I, I, I, I]),
         "nbd_jk": (I, [P, I, P, P, P, P, P]),

@@ -142,6 +142,31 @@ class B200Context:
         self.naux_local = naux - global_row0 if naux_local < 0 else int(naux_local)
         return nao, naux
 
+    # -- exchange-correlation (UKS objects) ------------------------------------------------------------------
+    XC_CODES = {"b3lyp": 1, "lda": 2, "lda,vwn_rpa": 2}
+
+    def xc_setup(self, xc: str, atm, bas, env, coords, weights):
+        """AO values / gradients of the orbital basis (libcint arrays) on the caller's grid, resident on the device."""
+        code = self.XC_CODES.get(str(xc).lower())
+        if code is None:
+            raise NbdError(-4, f"xc functional {xc!r} is not implemented on the device (available: {sorted(self.XC_CODES)})")
+        atm, bas, env = self._basis_arrays(atm, bas, env)
+        coords, weights = f64(coords), f64(weights)
+        if coords.ndim != 2 or coords.shape[1] != 3 or weights.shape != (coords.shape[0],):
+            raise ValueError("coords must be (ngrid, 3) and weights (ngrid,)")
+        self._ck(self._lib.nbd_xc_setup(self._h, code, ptr(atm), atm.shape[0], ptr(bas), bas.shape[0], ptr(env), env.size,
+                                        coords.shape[0], ptr(coords), ptr(weights)))
+
+    def xc_nr_uks(self, dm):
+        """(nelec [2], exc, vxc [2, nao, nao]) = NumInt.nr_uks for the spin densities dm [2, nao, nao]."""
+        dm = f64(np.asarray(dm).reshape(2, self.nao, self.nao))
+        nelec, exc, vxc = np.zeros(2), C.c_double(), np.empty((2, self.nao, self.nao))
+        self._ck(self._lib.nbd_xc_nr_uks(self._h, ptr(dm), ptr(nelec), C.cast(C.byref(exc), C.c_void_p), ptr(vxc)))
+        return nelec, exc.value, vxc
+
+    def scf_set_xc(self, on: bool):
+        self._ck(self._lib.nbd_scf_set_xc(self._h, int(bool(on))))
+
     # -- J/K -------------------------------------------------------------------------------------
     def jk_orbitals(self, orbs, signs=None, with_j=True, with_k=True):
         """orbs: list of (nao, ncol) scaled occupied-orbital blocks; returns (vj, vk) of shape (nset, nao, nao)."""

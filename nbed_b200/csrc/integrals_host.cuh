@@ -65,7 +65,7 @@ struct DfBasis {
 // libcint (atm, bas, env) of the concatenated mol + auxmol -> segmented shell tables (one entry per contraction)
 static DfBasis parse_basis(const int* atm, int natm, const int* bas, int nbas, const double* env, int nenv, int nbas_ao) {
   DfBasis B;
-  NBD_REQUIRE(atm && bas && env && natm > 0 && nbas > 0 && nbas_ao > 0 && nbas_ao < nbas, NBD_ERR_ARG, "bad basis arrays");
+  NBD_REQUIRE(atm && bas && env && natm > 0 && nbas > 0 && nbas_ao > 0 && nbas_ao <= nbas, NBD_ERR_ARG, "bad basis arrays");
   for (int ib = 0; ib < nbas; ++ib) {
     const int* b = bas + (size_t)ib * CINT_BAS_SLOTS;
     const int ia = b[CINT_ATOM_OF], l = b[CINT_ANG_OF], np = b[CINT_NPRIM_OF], nc = b[CINT_NCTR_OF];
@@ -101,6 +101,7 @@ struct DfDevice {
 
 // (P | mu >= nu) [naux][npair] and (P|Q) [naux][naux] on the device
 static void df_integrals_device(nbd_ctx* c, const DfBasis& B, const double* env, int nenv, DfDevice& D) {
+  NBD_REQUIRE(!B.aux.empty(), NBD_ERR_ARG, "no auxiliary shells: nbas_ao must be smaller than nbas");
   const long npair = (long)B.nao * (B.nao + 1) / 2;
   D.ao.ensure(B.ao.size());
   D.aux.ensure(B.aux.size());

@@ -18,6 +18,7 @@
 #include "host_util.cuh"
 #include "jk.cuh"
 #include "scf_kernels.cuh"
+#include "integrals.cuh"
 #include "subspace.cuh"
 
 using namespace nbd;
@@ -114,6 +115,17 @@ struct KGroup {
 struct HuzLoop {
   int Ntot = 0;
   std::vector<KGroup> groups;
+  bool veff_valid = false;  // Kohn-Sham loop: F / vhf already hold get_veff of the current density
+};
+
+// exchange-correlation stage (xc.cuh / xc_host.cuh): resident AO values on the caller's grid + workspaces
+struct XcState {
+  bool ready = false, on = false;
+  int code = 0, ng = 0, ng_user = 0;
+  double hyb = 0.0;
+  double ecoul = 0.0, exc = 0.0;  // of the last Kohn-Sham get_veff (the .ecoul / .exc tags the reference reads)
+  DBuf<IntShell> shells;
+  DBuf<double> env, c2s, coords, w, ao, rho, grad, sigma, fx, TM, Vpart, V;
 };
 
 struct nbd_ctx {
@@ -130,6 +142,7 @@ struct nbd_ctx {
   int overlap = 1;
   int eig_threads = 1;  // second spin's full eigensolve issued from a helper thread on the side stream
   int dist_eig = 1;
+  int ks_energy = 0;  // mu / kernel() path with XC on: 1 = pyscf's KS energy_elec (e1 + ecoul + exc), 0 = nbed's patched energy_elec (e1 + tr(vhf D) / 2)
   int dist_orth = 1;  // multi-rank: every rank forms its row block of F' = X F X, one all-gather assembles it
   int gemm_tile = 0;      // tuning: force the GEMM tile size (0 = heuristic)
   int jpass_variant = 0;  // 0: TMA-fed persistent pass 2, 1: LDG streaming pass 2
@@ -199,6 +212,8 @@ struct nbd_ctx {
 
   // ---- ao2mo ----
   DBuf<double> mo_c, Lbuf, eri, eri_phys;
+
+  XcState xc;
 };
 
 #define LAUNCH_CHECK(ctx)               \
@@ -820,6 +835,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "eig_threads") c->eig_threads = (int)value;
   else if (k == "dist_eig") c->dist_eig = (int)value;
   else if (k == "dist_orth") c->dist_orth = (int)value;
+  else if (k == "ks_energy") c->ks_energy = (int)value;
   else if (k == "panel_stages") c->panel_stages = (int)value;
   else if (k == "panel_hybrid") c->panel_hybrid = (int)value;
   else if (k == "jpass_variant") c->jpass_variant = (int)value;
@@ -1119,6 +1135,7 @@ extern "C" int nbd_jk_dm(nbd_ctx* c, int nset, const double* dm, double* vj, dou
 }
 
 #include "subspace_host.cuh"
+#include "integrals_host.cuh"
+#include "xc_host.cuh"
 #include "scf_host.cuh"
 #include "ao2mo_host.cuh"
-#include "integrals_host.cuh"

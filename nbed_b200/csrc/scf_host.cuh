@@ -23,18 +23,41 @@ static int scf_stage_occupied(nbd_ctx* c) {
   return tot;
 }
 
-// J/K of the staged orbital block -> vhf_s = J - kscale K_s and F_s = heff_s + vhf_s
+// J/K of the staged orbital block -> vhf_s = J - kscale K_s and F_s = heff_s + vhf_s.
+// Kohn-Sham objects (c->xc.on; pyscf/dft/uks.py:get_veff as reached from huzinaga_scf.py:55,156): kscale = the hybrid
+// fraction, vhf_s += V_xc,s[D] for the density in c->D (the one the staged orbitals belong to), and the scalars the
+// reference reads from the result's tags: ecoul = tr((D_a + D_b) J) / 2, exc = int f - hyb sum_s tr(D_s K_s) / 2.
 static void scf_build_fock(nbd_ctx* c, int Ntot, const std::vector<KGroup>& groups) {
   const int n = c->nao;
   const long nn = (long)n * n;
   const int ns = c->nspin;
+  const bool ks = c->xc.on;
+  if (ks) NBD_REQUIRE(ns == 2, NBD_ERR_UNSUPPORTED, "the Kohn-Sham branch is spin-resolved (the reference's drivers build UKS objects, driver.py:289-313)");
   double* buf = c->d_jk.ensure((size_t)(1 + ns) * nn);
   std::vector<int> jbegin = {0, Ntot};
   jk_device(c, c->d_orb.p, c->d_wt.p, Ntot, 1, jbegin, buf, ns, groups, buf + nn);
   all_reduce(c, buf, (size_t)(1 + ns) * nn);
+  {
+    StageScope ts(c->timers, c->stream, "fock");
+    const double kscale = ks ? c->xc.hyb : (ns == 2 ? 1.0 : 0.5);
+    fock_from_heff_kernel<<<grid1(nn, 256), 256, 0, c->stream>>>(c->heff.p, buf, buf + nn, kscale, c->F.p, c->vhf.p, nn, ns);
+    LAUNCH_CHECK(c);
+  }
+  if (!ks) return;
+  double in3[3];
+  xc_eval_device(c, c->D.p, in3);
   StageScope ts(c->timers, c->stream, "fock");
-  fock_from_heff_kernel<<<grid1(nn, 256), 256, 0, c->stream>>>(c->heff.p, buf, buf + nn, ns == 2 ? 1.0 : 0.5, c->F.p, c->vhf.p, nn, ns);
+  xc_add_potential_kernel<<<grid1(2 * nn, 256), 256, 0, c->stream>>>(c->xc.V.p, c->F.p, c->vhf.p, 2 * nn);
   LAUNCH_CHECK(c);
+  double* out = c->red_out.ensure(64);
+  reduce_to(c, c->D.p, buf, nn, 0, n, out + 52);             // tr(D_a J)
+  reduce_to(c, c->D.p + nn, buf, nn, 0, n, out + 53);        // tr(D_b J)
+  reduce_to(c, c->D.p, buf + nn, 2 * nn, 0, n, out + 54);    // sum_s tr(D_s K_s)
+  double h[3];
+  d2h(c, h, out + 52, 3);
+  NBD_CUDA(cudaStreamSynchronize(c->stream));
+  c->xc.ecoul = 0.5 * (h[0] + h[1]);
+  c->xc.exc = in3[0] - 0.5 * c->xc.hyb * h[2];
 }
 static std::vector<KGroup> scf_occ_groups(const nbd_ctx* c) {
   std::vector<KGroup> g;
@@ -380,24 +403,30 @@ static void huz_initial(nbd_ctx* c, const double* dm0, HuzLoop& L) {
 }
 
 // one pass of the loop body (huzinaga_scf.py:154-201); out: per-spin energies and max_s ||dD_s||_F
+// Kohn-Sham objects (:176-180, calculate_ks_energy :36-62): the energy needs get_veff of the NEW density; the reference
+// then builds the same get_veff again at the top of the next cycle - here it is built once and reused (same numbers).
 static void huz_iteration(nbd_ctx* c, int iter, bool use_diis, HuzLoop& L, double* energy, double* norm_ddm) {
-  const long nn = (long)c->nao * c->nao;
-  scf_build_fock(c, L.Ntot, L.groups);                                // :156-157
+  const bool ks = c->xc.on;
+  if (!(ks && L.veff_valid)) scf_build_fock(c, L.Ntot, L.groups);     // :156-157
   scf_apply_huzinaga(c);                                              // :159-160
   if (use_diis && iter > 1) diis_update(c, c->diis, c->F.p, nullptr);  // :162-164
   scf_diagonalise_lowdin(c, true, true);                              // :166-169
   scf_make_density(c);                                                // :170-174
+  L.Ntot = scf_stage_occupied(c);
+  L.groups = scf_occ_groups(c);
+  if (ks) {
+    scf_build_fock(c, L.Ntot, L.groups);                              // :55  vhf_updated = get_veff(dm = new density)
+    L.veff_valid = true;
+  }
   double t[8];
   scf_traces(c, c->heff.p, c->vhf.p, c->Huz.p, true, t);              // :182-194
   double nd = 0.0;
   for (int s = 0; s < c->nspin; ++s) {
-    energy[s] = t[4 * s + 0] + 0.5 * t[4 * s + 1] + t[4 * s + 2];
+    energy[s] = ks ? (c->xc.ecoul + c->xc.exc) + t[4 * s + 0] + t[4 * s + 2]   // :56-61
+                   : t[4 * s + 0] + 0.5 * t[4 * s + 1] + t[4 * s + 2];
     nd = std::max(nd, std::sqrt(t[4 * s + 3]));
   }
   *norm_ddm = nd;
-  L.Ntot = scf_stage_occupied(c);
-  L.groups = scf_occ_groups(c);
-  (void)nn;
 }
 
 static void scf_export(nbd_ctx* c, double* mo_coeff, double* mo_energy, double* dm, double* extra, const double* d_extra) {
@@ -542,6 +571,7 @@ static double mu_energy(nbd_ctx* c, double e_nuc) {
     e1 += t[4 * s + 0];
     ec += t[4 * s + 1];
   }
+  if (c->xc.on && c->ks_energy) return e1 + c->xc.ecoul + c->xc.exc + e_nuc;  // pyscf/dft/rks.py:energy_elec
   return e1 + 0.5 * ec + e_nuc;
 }
 

@@ -158,7 +158,15 @@ class _B200SCF:
             dm0 = np.array(dm0)
         zero = np.zeros((2, n, n))
         self.ctx.scf_setup(self.nelec, self._s, h, zero, zero, NBD_MU_SHIFT, 0.0)
-        c, e, occ, dm, vhf, info = self.ctx.mu_scf(self.max_cycle, self.conv_tol, self.energy_nuc(), dm0)
+        is_ks = getattr(self, "is_ks", False)
+        self.ctx.scf_set_xc(is_ks)
+        # a Kohn-Sham object uses pyscf's own energy_elec (e1 + ecoul + exc) unless nbed has patched it (driver.py:522)
+        self.ctx.set_option("ks_energy", int(is_ks and "energy_elec" not in self.__dict__))
+        try:
+            c, e, occ, dm, vhf, info = self.ctx.mu_scf(self.max_cycle, self.conv_tol, self.energy_nuc(), dm0)
+        finally:
+            self.ctx.scf_set_xc(False)
+            self.ctx.set_option("ks_energy", 0)
         self.mo_coeff, self.mo_energy, self.mo_occ = c, e, occ
         self.e_tot, self.converged = info["e_tot"], info["converged"]
         self.scf_info = info
@@ -185,6 +193,61 @@ class B200UHF(_B200SCF):
 
     def energy_elec(self, dm=None, h1e=None, vhf=None):
         return energy_elec(self, dm, h1e, vhf)
+
+
+class B200UKS(B200UHF):
+    """``pyscf.dft.UKS(mol).density_fit()`` analogue: J/K from the device-resident 3-centre tensor, exchange-correlation
+    on the device over the caller's quadrature.
+
+    ``grids`` = (coords [ng, 3] in Bohr, weights [ng]) - PySCF's ``mf.grids.coords / mf.grids.weights``;
+    ``basis`` = (atm, bas, env) libcint arrays of the orbital basis (``mol._atm, mol._bas, mol._env``)."""
+
+    is_ks = True
+    HYB = {"b3lyp": 0.2, "lda": 0.0}
+
+    def __init__(self, ctx, ovlp, hcore, nelec, xc="b3lyp", grids=None, basis=None, **kw):
+        super().__init__(ctx, ovlp, hcore, nelec, **kw)
+        if grids is None or basis is None:
+            raise ValueError("B200UKS needs grids = (coords, weights) and basis = (atm, bas, env)")
+        self.xc = str(xc).lower()
+        self.grids, self.basis = grids, basis
+        ctx.xc_setup(self.xc, *basis, *grids)
+
+    def get_veff(self, mol=None, dm=None, dm_last=0, vhf_last=0, hermi=1):
+        """pyscf/dft/uks.py:get_veff: vxc + vj - hyb vk, tagged with ecoul / exc / vj / vk."""
+        if dm is None:
+            dm = self.make_rdm1()
+        if isinstance(dm, np.ndarray) and dm.ndim == 2:
+            dm = np.asarray((dm * 0.5, dm * 0.5))
+        _, exc, vxc = self.ctx.xc_nr_uks(np.asarray(dm))
+        hyb = self.HYB[self.xc]
+        if abs(hyb) < 1e-10:
+            vj = self.get_j(mol, dm, hermi)
+            vj = vj[0] + vj[1]
+            vxc = vxc + vj
+            vk = None
+        else:
+            vj, vk = self.get_jk(mol, dm, hermi)
+            vj = vj[0] + vj[1]
+            vk = vk * hyb
+            vxc = vxc + vj - vk
+            exc -= (np.einsum("ij,ji", dm[0], vk[0]).real + np.einsum("ij,ji", dm[1], vk[1]).real) * 0.5
+        ecoul = np.einsum("ij,ji", np.asarray(dm[0]) + np.asarray(dm[1]), vj).real * 0.5
+        return tag_array(vxc, ecoul=float(ecoul), exc=float(exc), vj=vj, vk=vk)
+
+    def energy_elec(self, dm=None, h1e=None, vhf=None):
+        """pyscf/dft/rks.py:energy_elec on the total density: e1 + ecoul + exc."""
+        if dm is None:
+            dm = self.make_rdm1()
+        if h1e is None:
+            h1e = self.get_hcore()
+        if vhf is None or getattr(vhf, "ecoul", None) is None:
+            vhf = self.get_veff(dm=dm)
+        h1e, d = np.asarray(h1e), np.asarray(dm)
+        e1 = np.einsum("sij,sji->", h1e, d).real if h1e.ndim == 3 else np.einsum("ij,ji->", h1e, d[0] + d[1]).real
+        e2 = vhf.ecoul + vhf.exc
+        self.scf_summary.update(e1=float(e1), coul=vhf.ecoul, exc=vhf.exc)
+        return float(e1 + e2), float(e2)
 
 
 class B200RHF(_B200SCF):
@@ -268,8 +331,12 @@ def huzinaga_scf(scf_method, embedding_potential, dm_environment_occupied, dm_en
         if gv.shape != g.shape:
             raise ValueError("dm_environment_virtual must have the shape of dm_environment_occupied")
         ctx.scf_set_virtual_projector(gv)
-    c, e, dm, huz, info = ctx.huzinaga_scf(scf_method.max_cycle, scf_method.conv_tol, dm_conv_tol, use_DIIS,
-                                           dm0=dm_initial_guess)
+    ctx.scf_set_xc(getattr(scf_method, "is_ks", False))  # UKS objects: :55-62,176-180
+    try:
+        c, e, dm, huz, info = ctx.huzinaga_scf(scf_method.max_cycle, scf_method.conv_tol, dm_conv_tol, use_DIIS,
+                                               dm0=dm_initial_guess)
+    finally:
+        ctx.scf_set_xc(False)
     occ = scf_method.get_occ(e, c)
     dm = tag_array(dm, mo_coeff=c, mo_occ=occ)
     if return_info:
@@ -305,7 +372,14 @@ def mu_embed(localized_scf, embedding_potential, dm_enviro, mu_level_shift: floa
     ctx = localized_scf.ctx
     hcore_std = localized_scf.get_hcore()
     ctx.scf_setup(localized_scf.nelec, s, hcore_std, v, g, NBD_MU_SHIFT, mu_level_shift)
-    c, e, occ, dm, vhf, info = ctx.mu_scf(localized_scf.max_cycle, localized_scf.conv_tol, localized_scf.energy_nuc(), dm0)
+    # UKS objects: get_veff carries V_xc; the energy stays nbed's patched energy_elec (driver.py:521-522 patches it for
+    # every rank-3 potential, Kohn-Sham objects included): e1 + tr(vhf D) / 2
+    ctx.scf_set_xc(getattr(localized_scf, "is_ks", False))
+    ctx.set_option("ks_energy", 0)
+    try:
+        c, e, occ, dm, vhf, info = ctx.mu_scf(localized_scf.max_cycle, localized_scf.conv_tol, localized_scf.energy_nuc(), dm0)
+    finally:
+        ctx.scf_set_xc(False)
     proj = np.einsum("ij,...jk,kl->...il", s, g, s)
     v_emb = mu_level_shift * proj + v
     localized_scf.get_hcore = lambda *args: hcore_std + v_emb  # :529

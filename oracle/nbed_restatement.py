@@ -2,8 +2,9 @@
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 The SCF object passed in is any object satisfying the protocol of SURVEY.md §8(b); the oracle uses
-``oracle.pyscf_restatement.DFUHF`` / ``DFRHF``.  Validated against the reference's unmodified code in
-``tests/test_oracle_vs_reference.py`` (dev container) and frozen in ``tests/golden``.
+``oracle.pyscf_restatement.DFUHF`` / ``DFRHF``.  Validated against the reference's unmodified code by ``tests/golden/make_golden.py`` /
+``make_golden_fullsize.py`` (dev container: they import /root/reference behind oracle/stubs.py) and frozen in
+``tests/golden``; ``tests/test_golden.py`` holds the restatement to those outputs.
 """
 from __future__ import annotations
 
@@ -41,7 +42,8 @@ def huzinaga_scf(
     use_DIIS=True,
     trace=None,
 ):
-    """Same iterate sequence as the reference loop (HF objects; the KS branch needs XC and is out of scope).
+    """Same iterate sequence as the reference loop, Hartree-Fock objects and - ``scf_method.is_ks`` - Kohn-Sham objects
+    (the isinstance test of :176 selects calculate_ks_energy, :36-62, which calls get_veff a second time per cycle).
 
     ``trace`` (list) receives per-cycle dicts {energy, norm_dm_diff} for iterate-level parity tests.
     """
@@ -77,8 +79,14 @@ def huzinaga_scf(
         mo_occ = scf_method.get_occ(mo_energy, mo_coeff_std)
         dm_mat_old = density_matrix
         density_matrix = scf_method.make_rdm1(mo_coeff=mo_coeff_std, mo_occ=mo_occ)  # :174
-        hamiltonian = scf_method.get_hcore() + embedding_potential + 0.5 * vhf + huzinaga_op  # :182-184
-        scf_energy = np.einsum("...ij,...ji->...", hamiltonian, density_matrix)  # :185
+        if getattr(scf_method, "is_ks", False):  # :176-180 -> calculate_ks_energy, :55-61
+            vhf_updated = scf_method.get_veff(dm=density_matrix)
+            scf_energy = vhf_updated.ecoul + vhf_updated.exc
+            scf_energy = scf_energy + np.einsum(
+                "...ij, ...ji->...", density_matrix, (scf_method.get_hcore() + huzinaga_op + embedding_potential))
+        else:
+            hamiltonian = scf_method.get_hcore() + embedding_potential + 0.5 * vhf + huzinaga_op  # :182-184
+            scf_energy = np.einsum("...ij,...ji->...", hamiltonian, density_matrix)  # :185
         run_diff = np.max(np.abs(scf_energy - scf_energy_prev))  # :191
         norm_dm_diff = np.max(np.linalg.norm(density_matrix - dm_mat_old, axis=(-2, -1)))  # :192-194
         if trace is not None:

@@ -12,6 +12,7 @@ import sys
 import types
 
 from . import pyscf_restatement as ps
+from . import xc_restatement as xcr
 
 REFERENCE_ROOT = "/root/reference"
 
@@ -43,8 +44,9 @@ class _RKS(StreamObject):
     pass
 
 
-class _UKS(StreamObject):
-    pass
+class _UKS(xcr.DFUKS, StreamObject):
+    """Stands in for pyscf.dft.uks.UKS: passes the reference's isinstance test (huzinaga_scf.py:176) and provides
+    get_veff with the .ecoul / .exc tags that calculate_ks_energy reads (:55-56)."""
 
 
 class _ROHF(StreamObject):
@@ -111,5 +113,5 @@ def install():
 
 def make_scf(kind: str, ovlp, hcore, cderi, nelec, **kw):
     """A stub-typed SCF object that passes the reference's ``isinstance`` checks (huzinaga_scf.py:176,181)."""
-    cls = {"rhf": _RHF, "uhf": _UHF}[kind]
+    cls = {"rhf": _RHF, "uhf": _UHF, "uks": _UKS}[kind]
     return cls(ovlp, hcore, cderi, nelec, **kw)

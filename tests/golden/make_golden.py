@@ -97,7 +97,56 @@ def reference_runs():
     return out
 
 
+def ks_problem():
+    """water / STO-3G with B3LYP on a fixed Becke grid: global UKS, then the O 1s orbital as frozen environment with
+    the DFT-in-DFT embedding potential veff[g_act + g_env] - veff[g_act] (nbed/driver.py:847-849).  Shared with the tests."""
+    import scipy.linalg
+
+    from oracle import gto_restatement as g
+    from oracle import pyscf_restatement as ps
+    from oracle import xc_restatement as xc
+
+    atoms = g.parse_xyz(open(os.path.join(HERE, "water.xyz")).read())
+    w = np.load(os.path.join(HERE, "water_sto3g.npz"))
+    s, h = w["S"], w["hcore"]
+    cd = ps.cholesky_eri_exact(w["eri"])
+    atm, bas, env = g.make_env(atoms, gi.STO3G)
+    coords, wts = xc.becke_grid(atoms, 50, 14, 28)
+    ao = xc.eval_ao(g.shells_from_env(atm, bas, env), coords)
+    mf = xc.DFUKS(s, h, cd, (5, 5), ao, wts, "b3lyp", e_nuc=float(w["e_nuc"]), max_cycle=50, conv_tol=1e-10)
+    _, c = scipy.linalg.eigh(h, s)
+    dm0 = np.array([c[:, :5] @ c[:, :5].T] * 2)
+    conv, e_tot, _, c0, _ = ps.scf_kernel(mf, conv_tol=1e-10, dm0=dm0)
+    c_env = np.array([c0[0][:, :1], c0[1][:, :1]])
+    dm_env = c_env @ c_env.swapaxes(-1, -2)
+    dm_act = np.array([c0[k][:, 1:5] @ c0[k][:, 1:5].T for k in range(2)])
+    v_emb = np.asarray(mf.get_veff(dm=dm_act + dm_env)) - np.asarray(mf.get_veff(dm=dm_act))
+    return dict(atoms=atoms, s=s, h=h, cderi=cd, basis=(atm, bas, env), coords=coords, weights=wts, ao=ao, dm0=dm0,
+                e_nuc=float(w["e_nuc"]), global_ks=mf, global_conv=conv, global_e_tot=e_tot, c_env=c_env, dm_env=dm_env,
+                v_emb=v_emb)
+
+
+def reference_runs_ks():
+    """The Kohn-Sham branch of the UNMODIFIED reference loop (huzinaga_scf.py:176-180, calculate_ks_energy :36-62) over
+    the stub UKS object of oracle/stubs.py (DF J/K + the XC restatement) -> reference_runs_ks.npz."""
+    stubs.install()
+    from nbed.scf.huzinaga_scf import huzinaga_scf
+
+    p = ks_problem()
+    act = stubs.make_scf("uks", p["s"], p["h"], p["cderi"], (4, 4), ao=p["ao"], weights=p["weights"], xc="b3lyp",
+                         max_cycle=40, conv_tol=1e-9)
+    c, e, d, hz, conv = huzinaga_scf(act, p["v_emb"], p["dm_env"], dm_conv_tol=1e-7)
+    out = dict(global_e_tot=p["global_e_tot"], global_energy_elec=np.array(p["global_ks"].energy_elec()),
+               ref_global_e_tot=-75.3091447400438, ref_global_energy_elec=np.array([-84.59485896172163, 37.93302591280513]),
+               v_emb=p["v_emb"], c_env=p["c_env"], ks_e=e, ks_dm=np.asarray(d), ks_huz=hz, ks_conv=conv,
+               ks_n_veff=act.n_xc_builds, ngrid=len(p["weights"]))
+    np.savez_compressed(os.path.join(HERE, "reference_runs_ks.npz"), **out)
+    return out
+
+
 if __name__ == "__main__":
     water()
+    ok = reference_runs_ks()
+    print("KS fixture: global E =", ok["global_e_tot"], "reference golden", ok["ref_global_e_tot"], "veff builds", ok["ks_n_veff"])
     o = reference_runs()
     print("written:", sorted(os.listdir(HERE)), len(o), "arrays")

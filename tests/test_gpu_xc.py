@@ -1,0 +1,120 @@
+"""GPU parity: exchange-correlation on the device (nbd_xc_setup / nbd_xc_nr_uks) and the Kohn-Sham branches of the
+embedded-SCF loops, against the oracle (oracle/xc_restatement.py, pinned on the reference's golden B3LYP energy) and
+against the fixture written by the UNMODIFIED reference's Kohn-Sham Huzinaga loop (tests/golden/reference_runs_ks.npz)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from nbed_b200 import B200UHF, B200UKS, LocalizedSystem, NbdError, huzinaga_scf, mu_embed
+from oracle import gto_restatement as g
+from oracle import nbed_restatement as nr
+from oracle import pyscf_restatement as ps
+from oracle import xc_restatement as xcr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ksp():
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.ks_problem()
+
+
+def test_nr_uks_spin_polarised_on_d_functions(ctx):
+    """numint.nr_uks on the device: water / cc-pVDZ (s, p, d functions), spin-polarised random densities (zeta != 0,
+    all five derivative channels), B3LYP and the LDA code path: nelec, exc, vxc against the oracle."""
+    atoms = g.parse_xyz(open(os.path.join(GOLD, "water.xyz")).read())
+    atm, bas, env = g.make_env(atoms, g.CCPVDZ)
+    sh = g.shells_from_env(atm, bas, env)
+    coords, wts = xcr.becke_grid(atoms, 30, 10, 20)  # 18000 points; not a multiple of the device's slab size
+    ao = xcr.eval_ao(sh, coords)
+    s, _, _ = g.int1e_sph(sh, atoms)
+    rng = np.random.default_rng(2)
+    w, v = np.linalg.eigh(s)
+    x = (v / np.sqrt(w)) @ v.T
+    q, _ = np.linalg.qr(rng.normal(size=(24, 24)))
+    c = x @ q
+    dm = np.array([c[:, :6] @ c[:, :6].T, c[:, 3:7] @ c[:, 3:7].T])  # 6 alpha, 4 beta electrons
+    ctx.cderi_alloc(24, 1)
+    for name in ("b3lyp", "lda"):
+        ctx.xc_setup(name, atm, bas, env, coords, wts)
+        n1, exc1, v1 = ctx.xc_nr_uks(dm)
+        n0, exc0, v0 = xcr.nr_uks(name, ao, wts, dm)
+        assert np.abs(n1 - n0).max() < 1e-11 and abs(n0[0] - 6) < 1e-2 and abs(n0[1] - 4) < 1e-2
+        assert abs(exc1 - exc0) < 1e-11 * max(1.0, abs(exc0)), (name, exc1, exc0)
+        assert np.abs(v1 - v0).max() < 1e-10, (name, np.abs(v1 - v0).max())
+        assert np.abs(v1 - v1.transpose(0, 2, 1)).max() < 1e-13
+    with pytest.raises(NbdError) as ei:
+        ctx.xc_setup("pbe", atm, bas, env, coords, wts)
+    assert ei.value.code == -4
+
+
+def test_global_b3lyp_kernel_reproduces_the_reference_golden(ctx, ksp):
+    """dft.UKS(mol).kernel() of the reference's _global_ks (driver.py:163-181) as B200UKS.kernel(): same energy as the
+    oracle on the same grid to 1e-8 Ha, and the reference's golden -75.3091447400438 (PySCF's own grid) to 1e-6."""
+    p = ksp
+    ctx.load_cderi(p["cderi"])
+    mf = B200UKS(ctx, p["s"], p["h"], (5, 5), xc="b3lyp", grids=(p["coords"], p["weights"]), basis=p["basis"],
+                 e_nuc=p["e_nuc"], max_cycle=50, conv_tol=1e-10)
+    e = mf.kernel(dm0=p["dm0"])
+    assert mf.converged and abs(e - p["global_e_tot"]) < 1e-8
+    assert abs(e - (-75.3091447400438)) < 1e-6  # tests/test_driver.py:45
+    ee = mf.energy_elec()
+    ref = p["global_ks"].energy_elec()
+    assert abs(ee[0] - ref[0]) < 1e-8 and abs(ee[1] - ref[1]) < 1e-8
+    # get_veff carries the tags the reference reads (huzinaga_scf.py:56; driver.py:363-364)
+    dm = mf.make_rdm1()
+    v1, v0 = mf.get_veff(dm=dm), p["global_ks"].get_veff(dm=np.asarray(dm))
+    assert abs(v1.ecoul - v0.ecoul) < 1e-9 and abs(v1.exc - v0.exc) < 1e-9 and np.abs(np.asarray(v1) - np.asarray(v0)).max() < 1e-9
+
+
+def test_kohn_sham_huzinaga_loop_against_the_unmodified_reference(ctx, ksp):
+    """DFT-in-DFT: the Kohn-Sham branch of huzinaga_scf (:176-180, calculate_ks_energy :36-62) on the device against the
+    fixture of the unmodified reference loop - density, Huzinaga operator, occupied orbital energies, and the embedded
+    density + environment == global Kohn-Sham density."""
+    p = ksp
+    fx = np.load(os.path.join(GOLD, "reference_runs_ks.npz"))
+    ctx.load_cderi(p["cderi"])
+    act = B200UKS(ctx, p["s"], p["h"], (4, 4), xc="b3lyp", grids=(p["coords"], p["weights"]), basis=p["basis"],
+                  max_cycle=40, conv_tol=1e-9)
+    ls = LocalizedSystem(np.arange(1, 5), np.arange(1), p["c_env"][:, :, :0], p["c_env"], p["c_env"])
+    c, e, d, hz, conv, info = huzinaga_scf(act, p["v_emb"], ls.dm_enviro, dm_conv_tol=1e-7, return_info=True)
+    assert conv == bool(fx["ks_conv"])
+    assert np.abs(np.asarray(d) - fx["ks_dm"]).max() < 1e-8 and np.abs(hz - fx["ks_huz"]).max() < 1e-7
+    assert np.abs(e[:, :4] - fx["ks_e"][:, :4]).max() < 1e-8
+    # per-cycle energies against the oracle restatement (the reference function does not return them)
+    ref = xcr.DFUKS(p["s"], p["h"], p["cderi"], (4, 4), p["ao"], p["weights"], "b3lyp", max_cycle=40, conv_tol=1e-9)
+    tr = []
+    nr.huzinaga_scf(ref, p["v_emb"], p["dm_env"], dm_conv_tol=1e-7, trace=tr)
+    assert abs(info["cycles"] - len(tr)) <= 1
+    k = min(info["cycles"], len(tr))
+    assert np.abs(info["trace"][:k, :2] - np.array([t["energy"] for t in tr[:k]])).max() < 1e-8
+    assert np.abs(np.asarray(d) + p["dm_env"] - np.asarray(p["global_ks"].make_rdm1())).max() < 1e-6
+    # the same object type check as the reference: a Hartree-Fock object on the same inputs takes the HF branch
+    hf = B200UHF(ctx, p["s"], p["h"], (4, 4), max_cycle=40, conv_tol=1e-9)
+    _, _, d_hf, _, _ = huzinaga_scf(hf, p["v_emb"], ls.dm_enviro, dm_conv_tol=1e-7)
+    assert np.abs(np.asarray(d_hf) - np.asarray(d)).max() > 1e-4
+
+
+def test_kohn_sham_mu_shift_path(ctx, ksp):
+    """mu-shift embedding of a UKS object (BASELINE config 1: B3LYP, mu projector): get_veff carries V_xc, the energy is
+    nbed's patched energy_elec (driver.py:521-522 patches every rank-3 case, Kohn-Sham objects included)."""
+    p = ksp
+    mu = 1e6
+    ref = xcr.DFUKS(p["s"], p["h"], p["cderi"], (4, 4), p["ao"], p["weights"], "b3lyp", e_nuc=p["e_nuc"], max_cycle=50, conv_tol=1e-9)
+    dm0 = np.array([p["dm0"][0] * 0.8, p["dm0"][1] * 0.8])
+    tr = []
+    ref, v_ref = nr.mu_embed(ref, p["v_emb"], p["dm_env"], mu_level_shift=mu, dm0=dm0, trace=tr)
+    ctx.load_cderi(p["cderi"])
+    mf = B200UKS(ctx, p["s"], p["h"], (4, 4), xc="b3lyp", grids=(p["coords"], p["weights"]), basis=p["basis"],
+                 e_nuc=p["e_nuc"], max_cycle=50, conv_tol=1e-9)
+    mf, v_emb, info = mu_embed(mf, p["v_emb"], p["dm_env"], mu_level_shift=mu, dm0=dm0, return_info=True)
+    assert mf.converged == ref.converged and len(info["trace"]) == len(tr)
+    assert max(abs(info["trace"][k, 0] - t[0]) for k, t in enumerate(tr)) < 1e-8
+    assert abs(mf.e_tot - ref.e_tot) < 1e-8 and np.abs(v_emb - v_ref).max() < 1e-9
+    assert np.abs(mf.make_rdm1() - np.asarray(ref.make_rdm1())).max() < 1e-7
