@@ -75,6 +75,18 @@ __device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, uint
       : "memory");
 }
 
+__device__ __forceinline__ unsigned int smid() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+
+// Spatial split of two co-running grids: exactly `p` of the `nsm` SMs, evenly spread over the SM ids (and with them over
+// the GPCs), belong to group 1; the rest to group 0.
+__device__ __forceinline__ bool sm_in_group1(unsigned int sm, int p, int nsm) {
+  return ((sm + 1u) * (unsigned)p) / (unsigned)nsm != (sm * (unsigned)p) / (unsigned)nsm;
+}
+
 // ---- thread-block clusters: barrier + distributed shared memory -----------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

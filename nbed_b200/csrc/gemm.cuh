@@ -226,6 +226,9 @@ inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g) {
   if (first_use_on_current_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return e;
+    // GEMMs co-run with other grids (the K Gram next to pass 2): keep the SM at its largest shared-memory carveout
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch > 0 ? g.batch : 1);
   if (g.pdl) {

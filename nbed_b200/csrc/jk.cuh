@@ -543,6 +543,9 @@ __global__ void __launch_bounds__(256) j_pass_kernel(const double2* __restrict__
 // ~64 KiB in flight per CTA with 160 threads and 17 registers' worth of accumulators, so it reaches HBM speed next
 // to the tensor-bound K Gram (whose CTAs leave little room for the register-hungry LDG version above).
 constexpr int JP_STAGES = 7;  // 2 CTAs of 57 KiB fit next to one 101 KiB Gram CTA on an SM
+constexpr int JP_STAGES_ALONE = 7;  // ring depth on an SM that runs only pass 2 (3 CTAs; 9 stages measured no faster)
+constexpr int JP_MAX_STAGES = 12;
+constexpr int JP_HEADER = 384;  // full[12] | empty[12] | item_q[16] | pad; the ring starts 128-byte aligned
 constexpr int JP_CONSUMERS = 4;    // consumer warps (8 lighter warps were measured slower next to the Gram)
 constexpr int JP_THREADS = (JP_CONSUMERS + 1) * 32;
 constexpr int JP_Q = 512 / (JP_CONSUMERS * 32);  // double2 per thread per tile
@@ -550,19 +553,28 @@ constexpr int JP_Q = 512 / (JP_CONSUMERS * 32);  // double2 per thread per tile
 // kernel run at very different speeds depending on what shares their SM, and a static split would wait for the
 // slowest.  The producer lane draws the item, publishes it through shared memory ahead of the item's first tile
 // (the mbarrier completion orders the two), and releases the consumers with a bare arrival when the queue is dry.
-template <int NSET>
+// SAFE: the stage is released only after every lane's shared-memory loads of the tile have RETURNED (a warp vote over a
+// value computed from the loaded registers gates the arrival).  Without it the arrival is issued while the last LDS
+// of the tile may still be in flight (the FMAs that consume them are scheduled behind it); next to the 8-warp
+// stream-K Gram CTA of syrk.cuh that produced wrong tiles (tools/race_probe*.py, profiles/r02_pass2_race.md).
+template <int NSET, bool SAFE = true>
 __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __restrict__ Bt, const double* __restrict__ rho,
                                                                 double* __restrict__ part, int ntiles, int naux,
                                                                 int nsplit, int rows_per_split,
-                                                                unsigned int* __restrict__ next_item) {
+                                                                unsigned int* __restrict__ next_item, int sm_mod,
+                                                                int sm_keep, int nst) {
+  // spatial split of the pair (pass 2 on some SMs, the K Gram on the others): CTAs that land on an SM of the other
+  // group retire at once; the dynamic item queue hands all the work to the CTAs that stay
+  if (sm_mod > 0 && !sm_in_group1(smid(), sm_keep, sm_mod)) return;  // sm_keep of the sm_mod SMs run pass 2
   extern __shared__ __align__(128) unsigned char jsm[];
+  // ring depth nst <= JP_MAX_STAGES is a launch parameter: 7 next to the Gram, 9 when pass 2 has its SMs to itself
   uint64_t* full = reinterpret_cast<uint64_t*>(jsm);
-  uint64_t* empty = full + JP_STAGES;
-  volatile long* item_q = reinterpret_cast<volatile long*>(jsm + 128);  // [8] items in flight (>= ring depth + 1), indexed by sequence & 7
-  double* stages = reinterpret_cast<double*>(jsm + 256);
+  uint64_t* empty = full + JP_MAX_STAGES;
+  volatile long* item_q = reinterpret_cast<volatile long*>(jsm + 192);  // [16] items in flight (>= ring depth + 1), indexed by sequence & 15
+  double* stages = reinterpret_cast<double*>(jsm + JP_HEADER);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < JP_STAGES; ++s) {
+    for (int s = 0; s < nst; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], JP_CONSUMERS);
     }
@@ -582,8 +594,8 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
       for (unsigned int seq = 0;; ++seq) {
         long item = (long)atomicAdd(next_item, 1u);
         if (item >= nitems) item = -1;
-        if (!first) mbar_wait(&empty[st], ph);  // (also guarantees the consumers are done with item_q[seq & 7])
-        item_q[seq & 7] = item;
+        if (!first) mbar_wait(&empty[st], ph);  // (also guarantees the consumers are done with item_q[seq & 15])
+        item_q[seq & 15] = item;
         if (item < 0) {
           mbar_arrive(&full[st]);  // nothing to copy: release the consumers, which then read the sentinel
           break;
@@ -595,7 +607,7 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
           if (p > p0 && !first) mbar_wait(&empty[st], ph);
           mbar_expect_tx(&full[st], TILE_BYTES);
           bulk_g2s_stream(stages + (size_t)st * TILE_ELEMS, src, TILE_BYTES, &full[st], pol);
-          if (++st == JP_STAGES) {
+          if (++st == nst) {
             st = 0;
             ph ^= 1u;
             first = false;
@@ -609,7 +621,7 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
   uint32_t st = 0, ph = 0;
   for (unsigned int seq = 0;; ++seq) {
     mbar_wait_a(full_a + 8u * st, ph);  // first tile of the item (or the bare arrival of the sentinel)
-    const long item = item_q[seq & 7];
+    const long item = item_q[seq & 15];
     if (item < 0) break;
     const int sp = (int)(item / ntiles), k = (int)(item % ntiles);
     const int p0 = sp * rows_per_split, p1 = min(naux, p0 + rows_per_split);
@@ -627,8 +639,22 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
       double2 v[JP_Q];
 #pragma unroll
       for (int q = 0; q < JP_Q; ++q) v[q] = t2[tid + JP_CONSUMERS * 32 * q];
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(empty_a + 8u * st);
+      if (SAFE) {
+        // true for every payload a tensor can hold (the pattern is one particular NaN); the vote needs the high word of
+        // every loaded double2 in every lane, i.e. all four LDS of the warp have completed when it executes
+        bool landed = true;
+#pragma unroll
+        for (int q = 0; q < JP_Q; ++q) landed = landed && (__double2hiint(v[q].y) != 0x7ff8dead);
+        if (__all_sync(0xffffffffu, landed)) {
+          if (lane == 0) mbar_arrive_a(empty_a + 8u * st);
+        } else {  // same release; the branch only keeps the arrival control-dependent on the vote
+          __nanosleep(20);
+          if (lane == 0) mbar_arrive_a(empty_a + 8u * st);
+        }
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(empty_a + 8u * st);
+      }
 #pragma unroll
       for (int s = 0; s < NSET; ++s)
 #pragma unroll
@@ -636,7 +662,7 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
           acc[s][q].x = fma(r[s], v[q].x, acc[s][q].x);
           acc[s][q].y = fma(r[s], v[q].y, acc[s][q].y);
         }
-      if (++st == JP_STAGES) {
+      if (++st == (uint32_t)nst) {
         st = 0;
         ph ^= 1u;
       }

@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "gemm.cuh"
+#include "syrk.cuh"
 #include "host_util.cuh"
 #include "jk.cuh"
 #include "scf_kernels.cuh"
@@ -145,6 +146,14 @@ struct nbd_ctx {
   int ks_energy = 0;  // mu / kernel() path with XC on: 1 = pyscf's KS energy_elec (e1 + ecoul + exc), 0 = nbed's patched energy_elec (e1 + tr(vhf D) / 2)
   int dist_orth = 1;  // multi-rank: every rank forms its row block of F' = X F X, one all-gather assembles it
   int gemm_tile = 0;      // tuning: force the GEMM tile size (0 = heuristic)
+  int jpass_sm_mod = 0, jpass_sm_keep = 0;  // pass 2 only on SMs with smid % mod < keep (0 = everywhere)
+  int jpass_ctas_per_sm = 2;
+  int jpass_safe = 1;     // 0: pass 2 releases a ring stage before its loads are known to have returned (experiments)
+  int syrk_mode = 1;      // 1: the K Gram runs as the stream-K symmetric rank-k kernel (syrk.cuh) when the shape allows
+  int syrk_ctas = 0;      // CTAs of that kernel (0 = one per SM)
+  DBuf<double> syrk_ws;   // its partial tiles
+  DBuf<unsigned int> d_syrk_counter;
+  int pair_split = -1;    // > 0: pass 2 runs on this many SMs (3 CTAs each), the stream-K Gram on the others; 0: both everywhere; -1: automatic
   int jpass_variant = 0;  // 0: TMA-fed persistent pass 2, 1: LDG streaming pass 2
   int panel_stages = 0;  // tuning: cap on the ring depth of the panel kernel (0 = as many as fit)
   int panel_hybrid = 1;  // 9-10 trailing orbital columns: 8 on DMMA + 1-2 on the FMA pipe (0 = pad to 16 DMMA columns)
@@ -197,6 +206,8 @@ struct nbd_ctx {
   DBuf<double> sV, sY, sZ, sW, sAV, sPart, sG, sGpart, sM, sTheta, sRpart, sBound, sFprev, sLz;
   // spectral bounds of the filter: 0 = Gershgorin every cycle; 1 = Lanczos once, then widened by ||F'_k - F'_{k-1}||_F
   int sub_bound_mode = 1;
+  int sub_adaptive = 1;   // filter degree of a tracked block from the observed residual reduction per degree
+  double sub_rate = 0.0;  // slowest residual reduction per filter degree seen in the current SCF (0 = none yet)
   int sub_apply_variant = 0;  // 0: cluster split-K block product (4-CTA clusters, DSMEM reduction); 1: one CTA per 16 rows
   int sub_cold = 1;  // 1: the initial guess starts the block from pseudo-random vectors (no library eigensolve)
   bool sub_bounds_valid = false, sub_is_cold = false;
@@ -450,32 +461,51 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
   else cols.push_back({0, Ntot});
   // `behind` (optional) is issued directly behind the pass-2 kernel, before the partials are reduced: the K Gram of
   // the programmatic-launch mode below
+  // split_pair: the pair [pass 2 || stream-K Gram] of the last chunk runs on disjoint sets of SMs (option "pair_split" =
+  // number of pass-2 SMs).  Sharing SMs costs more than it gives: next to the Gram's 8 DMMA warps the pass-2 CTAs of an
+  // SM run at a quarter of their speed (6.9 ms for the pair, 4.6 + 3.0 ms alone), while 74 SMs with three pass-2 CTAs
+  // each already pull 6.05 TB/s (profiles/r02_pair_split.md).
+  bool split_pair = false;
+  int pair_p2 = 0;
   auto j_pass = [&](cudaStream_t st, const std::function<void()>& behind = nullptr) {
     StageScope ts(c->timers, st, "jk_j");
     const long E = (long)c->ntiles * TILE_ELEMS, E2 = E / 2;
     dim3 gf((n + 127) / 128, n);
     if (c->jpass_variant == 0) {
       // TMA-fed persistent kernel: items = (P-range, tile), drawn dynamically; ~16 items per CTA keep the tail short
-      const int ctas = 2 * c->sm_count;
+      const int p2 = split_pair ? std::min(pair_p2, c->sm_count - 1) : 0;
+      const int sm_mod = p2 > 0 ? c->sm_count : c->jpass_sm_mod, sm_keep = p2 > 0 ? p2 : c->jpass_sm_keep;
+      const int ctas = (p2 > 0 ? 3 : std::max(1, c->jpass_ctas_per_sm)) * c->sm_count;
       int nsplit = (int)std::max<long>(1, std::min<long>(std::min(naux, 16), (16L * ctas + c->ntiles - 1) / c->ntiles));
       const int rows_per_split = (naux + nsplit - 1) / nsplit;
       nsplit = (naux + rows_per_split - 1) / rows_per_split;
       unsigned int* counter = c->d_jcounter.ensure(4);
-      const size_t smem = 256 + (size_t)JP_STAGES * TILE_BYTES;
+      const int nst = p2 > 0 ? JP_STAGES_ALONE : JP_STAGES;
+      const size_t smem = JP_HEADER + (size_t)nst * TILE_BYTES, smem_max = JP_HEADER + (size_t)JP_MAX_STAGES * TILE_BYTES;
       static unsigned long long configured = 0;
       if (first_use_on_current_device(configured)) {
-        NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        // pass 2 shares its SMs with the K Gram: both ask for the largest shared-memory carveout
+        NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       }
       for (int s0 = 0; s0 < njset; s0 += 2) {
         const int ns = std::min(2, njset - s0);
         double* part = c->d_jpart.ensure((size_t)nsplit * ns * E);
         const int grid = (int)std::min<long>((long)c->ntiles * nsplit, ctas);
         NBD_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
-        if (ns == 2)
-          j_pass_tma_kernel<2><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter);
+        if (!c->jpass_safe) {  // legacy release order (experiments only)
+          NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+          NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+          if (ns == 2)
+            j_pass_tma_kernel<2, false><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter, sm_mod, sm_keep, nst);
+          else
+            j_pass_tma_kernel<1, false><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter, sm_mod, sm_keep, nst);
+        } else if (ns == 2)
+          j_pass_tma_kernel<2><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter, sm_mod, sm_keep, nst);
         else
-          j_pass_tma_kernel<1><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter);
+          j_pass_tma_kernel<1><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter, sm_mod, sm_keep, nst);
         LAUNCH_CHECK(c);
         if (behind && s0 == 0) behind();
         j_finalize_kernel<<<gf, 128, 0, st>>>(part, c->d_inv.p, d_J + (long)s0 * nn, n, c->nb, E, nsplit, ns);
@@ -515,6 +545,33 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
       LAUNCH_CHECK(c);
     }
     const bool fork = d_J && last && d_K && c->overlap;
+    {
+      bool all_syrk = c->syrk_mode && c->gemm_variant == 0 && !kgroups.empty();
+      for (size_t gi = 0; gi < kgroups.size() && all_syrk; ++gi) {
+        const int w = kgroups[gi].c1 - kgroups[gi].c0;
+        all_syrk = w > 0 && syrk_applicable(X + L.group_base[gi], n_ld, (long)np * w * n_ld, n, np * w, 1);
+      }
+      split_pair = fork && (c->overlap == 1 || c->overlap == 2) && c->pair_split != 0 && c->jpass_variant == 0 &&
+                   c->jpass_safe && njset <= 2 && all_syrk;
+      pair_p2 = c->pair_split;
+      if (split_pair && c->pair_split < 0) {
+        // Automatic split from the two kernels' own rates (measured on B200, profiles/r02_pair_split.md): an SM that
+        // runs only pass 2 streams ~90 GB/s; the Gram runs at ~0.8 of the FP64 tensor peak and loses ~5 % on a
+        // subset of the SMs.  p2 balances  bytes / (90 GB/s p2)  against  t_gram nsm / (nsm - p2).  When the Gram
+        // dominates (more than 1.5 x the HBM time of pass 2, e.g. 20 occupied orbitals per spin) sharing is better.
+        const double bytes = (double)np * c->ntiles * TILE_BYTES;  // one pass over the tiled tensor, whatever njset
+        double flops = 0.0;
+        const double nt = (n + SY_T - 1) / SY_T;
+        for (auto& g : kgroups) flops += nt * (nt + 1) / 2 * SY_T * SY_T * 2.0 * np * (g.c1 - g.c0);
+        const double t2 = bytes / 6.9e12, tg = flops / (0.8 * 37.2e12) * 148.0 / c->sm_count;
+        if (tg > 1.5 * t2) {
+          split_pair = false;
+        } else {
+          const double a = bytes / 90e9, b = 1.055 * tg * c->sm_count;
+          pair_p2 = std::max(c->sm_count / 4, std::min(c->sm_count * 3 / 5, (int)(0.94 * a * c->sm_count / (a + b) + 0.5)));
+        }
+      }
+    }
     if (fork) {
       // pass 2 (HBM-bound, no tensor work) runs on the side stream next to the tensor-bound K Gram of this chunk.
       // Launch order (option "overlap": 1 = pass 2 first, 2 = Gram first) made no measurable difference; with the
@@ -542,8 +599,27 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
         if (w > 0) {
           const double* Xa = X + L.group_base[gi];
           const long gstride = (long)np * w * n_ld;  // equal-width groups are laid out back to back
-          gemm(c, n, n, np * w, Xa, 1, n_ld, Xa, 1, n_ld, d_K + (long)g0.set * nn, n, g0.alpha,
-               k_started[g0.set] ? 1.0 : 0.0, batch, gstride, gstride, nn, /*lower=*/1, /*pdl=*/pdl_first ? 1 : 0);
+          // the stream-K kernel runs alone or on its own SMs; next to pass 2 on shared SMs the 64-tile GEMM is the
+          // better neighbour (C4 with 20 occupied orbitals per spin: pair 13.1 ms against 15.3 ms)
+          if (c->syrk_mode && !pdl_first && c->gemm_variant == 0 && (!fork || split_pair || c->syrk_mode == 2) &&
+              syrk_applicable(Xa, n_ld, gstride, n, np * w, batch)) {
+            SyrkArgs sa{};
+            sa.X = Xa; sa.ld = n_ld; sa.strideX = gstride;
+            sa.C = d_K + (long)g0.set * nn; sa.ldc = n; sa.strideC = nn;
+            sa.alpha = g0.alpha; sa.beta = k_started[g0.set] ? 1.0 : 0.0;
+            sa.n = n; sa.K = np * w; sa.batch = batch;
+            // spatial split of the pair (see j_pass below): the Gram's ranges = its share of the SMs
+            const int p2 = split_pair ? std::min(pair_p2, c->sm_count - 1) : 0;
+            const int ranges = c->syrk_ctas > 0 ? c->syrk_ctas : c->sm_count - p2;
+            sa.part = c->syrk_ws.ensure(syrk_plan(sa, ranges));
+            sa.counter = c->d_syrk_counter.ensure(4);
+            sa.sm_p2 = p2;
+            sa.nsm = c->sm_count;
+            NBD_CUDA(launch_syrk(c->stream, sa, p2 > 0 ? c->sm_count : std::min(ranges, 8 * c->sm_count), &c->launches));
+          } else {
+            gemm(c, n, n, np * w, Xa, 1, n_ld, Xa, 1, n_ld, d_K + (long)g0.set * nn, n, g0.alpha,
+                 k_started[g0.set] ? 1.0 : 0.0, batch, gstride, gstride, nn, /*lower=*/1, /*pdl=*/pdl_first ? 1 : 0);
+          }
           pdl_first = false;
           for (size_t q = gi; q < gj; ++q) k_started[kgroups[q].set] = true;
         }
@@ -840,10 +916,18 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "panel_hybrid") c->panel_hybrid = (int)value;
   else if (k == "jpass_variant") c->jpass_variant = (int)value;
   else if (k == "gemm_tile") c->gemm_tile = (int)value;
+  else if (k == "syrk") c->syrk_mode = (int)value;
+  else if (k == "pair_split") c->pair_split = (int)value;
+  else if (k == "jpass_safe") c->jpass_safe = (int)value;
+  else if (k == "jpass_sm_mod") c->jpass_sm_mod = (int)value;
+  else if (k == "jpass_sm_keep") c->jpass_sm_keep = (int)value;
+  else if (k == "jpass_ctas_per_sm") c->jpass_ctas_per_sm = (int)value;
+  else if (k == "syrk_ctas") c->syrk_ctas = (int)value;
   else if (k == "eig_mode") { c->eig_mode = (int)value; c->sub_valid = false; }
   else if (k == "sub_bound") { c->sub_bound_mode = (int)value; c->sub_bounds_valid = false; }
   else if (k == "sub_cold") c->sub_cold = (int)value;
   else if (k == "sub_apply_variant") c->sub_apply_variant = (int)value;
+  else if (k == "sub_adaptive") c->sub_adaptive = (int)value;
   else if (k == "sub_min_nao") { c->sub_min_nao = (int)value; c->sub_valid = false; }
   else return NBD_ERR_ARG;
   return NBD_OK;

@@ -386,6 +386,7 @@ static void huz_initial(nbd_ctx* c, const double* dm0, HuzLoop& L) {
   const long nn = (long)n * n;
   c->sub_valid = false;  // a new SCF never inherits the eigenvector block or the spectral bounds of the last one
   c->sub_bounds_valid = false;
+  c->sub_rate = 0.0;
   if (!dm0) {
     NBD_CUDA(cudaMemcpyAsync(c->F.p, c->heff.p, sizeof(double) * nn * c->nspin, cudaMemcpyDeviceToDevice, c->stream));
     scf_apply_huzinaga(c);

@@ -234,11 +234,19 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
   sub_spectral_bounds(c, Fp, bound, lowb);
   const double one[2] = {1.0, 1.0}, zero[2] = {0.0, 0.0};
   double* cur = c->sV.p;  // block to Rayleigh-Ritz next
+  double worst_prev = -1.0;
+  int deg_prev = 0;
   for (int outer = 0; outer < max_outer; ++outer) {
     if (outer > 0) {
       // scaled Chebyshev filter of degree `degree` damping [a, bound] (Zhou & Saad), per spin
       double e[2], cc[2], sig[2], sig1[2], al[2], be[2];
       int degree = max_degree;
+      // A tracked block late in the SCF starts close to converged: the residual reduction per filter degree observed
+      // earlier in this SCF (c->sub_rate, the slowest seen) tells how many degrees the remaining gap to `tol` needs.
+      if (!cold && c->sub_adaptive && c->sub_rate > 0.0 && c->sub_rate < 1.0 && worst_prev > 0.0) {
+        const double need = std::log(0.1 * tol / worst_prev) / std::log(c->sub_rate);
+        if (need < max_degree) degree = std::max(6, (int)std::ceil(need) + 2);
+      }
       for (int s = 0; s < ns; ++s) {
         const double a = c->sub_theta[s][KB - 1], a0 = c->sub_theta[s][0];
         const double bu = std::max(bound[s], a + 1e-3) + 1e-7 * std::fabs(bound[s]) + 1e-9;
@@ -246,6 +254,7 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
         // mode 0 has no estimate of the lowest eigenvalue: tracked blocks (theta_0 converged) take the full degree
         const double lmin = c->sub_bound_mode == 1 ? std::min(lowb[s], a0) : a0;
         degree = std::min(degree, chebyshev_degree(a, bu, lmin, 1e10, max_degree));
+        deg_prev = degree;
         e[s] = 0.5 * (bu - a);
         cc[s] = 0.5 * (bu + a);
         sig1[s] = e[s] / (a0 - cc[s]);
@@ -310,6 +319,9 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
     }
     ++c->sub_outer;
     if (worst < tol) return true;
+    if (!cold && outer > 0 && deg_prev > 0 && worst_prev > 0.0 && worst < worst_prev)
+      c->sub_rate = std::max(c->sub_rate, std::pow(worst / worst_prev, 1.0 / deg_prev));
+    worst_prev = worst;
   }
   return false;
 }

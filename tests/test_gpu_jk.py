@@ -161,3 +161,64 @@ def test_jk_hybrid_panel_matches_padded_panel(ctx):
             ctx.set_option("panel_hybrid", 1)
         scale = max(1.0, np.abs(vk0).max(), np.abs(vj0).max())
         assert np.abs(vj1 - vj0).max() <= 1e-13 * scale and np.abs(vk1 - vk0).max() <= 1e-13 * scale
+
+
+@pytest.mark.parametrize("n,naux,nocc", [(520, 12, (5, 5)), (1376, 7, (5, 4)), (1000, 9, (3, 0)), (640, 40, (13, 13))])
+def test_k_gram_stream_k_kernel(ctx, n, naux, nocc):
+    """The exchange Gram as the stream-K symmetric rank-k kernel (syrk.cuh; n >= 512, even) against the oracle and
+    against the generic lower-tile GEMM, for grids that cut every tile (one CTA per SM), that hold whole tiles per CTA
+    (7 CTAs: the direct-write path) and that have more CTAs than k-steps per tile."""
+    rng = np.random.default_rng(n + naux)
+    b = _cderi(n, naux)
+    ctx.load_cderi(b)
+    orbs = [rng.normal(size=(n, o)) / np.sqrt(n) for o in nocc]
+    rj, rk = ps.df_get_jk_occ(b, orbs)
+    scale = max(1.0, np.abs(rj).max(), np.abs(rk).max())
+    try:
+        ctx.set_option("syrk", 0)
+        _, vk_gemm = ctx.jk_orbitals(orbs)
+        ctx.set_option("syrk", 2)  # also next to pass 2 on shared SMs (1 = only alone or on its own SMs)
+        ctx.set_option("pair_split", 0)
+        for ctas in (0, 7, 1000):
+            ctx.set_option("syrk_ctas", ctas)
+            vj, vk = ctx.jk_orbitals(orbs)
+            assert np.abs(vk - rk).max() <= 1e-12 * scale, ctas
+            assert np.abs(vj - rj).max() <= 1e-12 * scale, ctas
+            assert np.abs(vk - vk_gemm).max() <= 1e-13 * scale, ctas
+            assert np.array_equal(vk, vk.transpose(0, 2, 1))
+    finally:
+        ctx.set_option("syrk", 1)
+        ctx.set_option("syrk_ctas", 0)
+        ctx.set_option("pair_split", -1)
+
+
+def test_pair_modes_agree_and_repeat(ctx):
+    """Pass 2 next to the stream-K Gram: shared SMs, spatial split (automatic and forced), serial.  Every mode must agree
+    with the serial result to rounding and repeat BIT-identically (regression test for the ring stage that was released
+    before its loads had returned, profiles/r02_pass2_race.md)."""
+    n, naux, nocc = 1376, 192, (5, 5)
+    rng = np.random.default_rng(5)
+    ctx.cderi_alloc(n, naux)
+    ctx.cderi_synth(3, 3.0 / np.sqrt(n * naux), 0)
+    orbs = [rng.normal(size=(n, o)) / np.sqrt(n) for o in nocc]
+    try:
+        ctx.set_option("overlap", 0)
+        j0, k0 = ctx.jk_orbitals(orbs)
+        ctx.set_option("overlap", 1)
+        scale = np.abs(k0).max()
+        for split, syrk in ((-1, 1), (0, 2), (0, 1), (60, 1), (100, 1)):
+            ctx.set_option("pair_split", split)
+            ctx.set_option("syrk", syrk)
+            j1 = k1 = None
+            for rep in range(5):
+                j, k = ctx.jk_orbitals(orbs)
+                if rep == 0:
+                    j1, k1 = j, k
+                # (the number of P-ranges of pass 2 follows its CTA count, so modes differ from each other by rounding)
+                assert np.array_equal(j, j1) and np.array_equal(k, k1), (split, syrk, rep, np.abs(j - j1).max())
+                assert np.abs(j - j0).max() <= 1e-14 * np.abs(j0).max(), (split, syrk, rep)
+                assert np.abs(k - k0).max() <= 1e-13 * scale, (split, syrk, rep)
+    finally:
+        ctx.set_option("overlap", 1)
+        ctx.set_option("pair_split", -1)
+        ctx.set_option("syrk", 1)
