@@ -12,6 +12,7 @@
 #include <cstring>
 #include <functional>
 #include <future>
+#include <thread>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -148,6 +149,8 @@ struct nbd_ctx {
   int gemm_tile = 0;      // tuning: force the GEMM tile size (0 = heuristic)
   int jpass_sm_mod = 0, jpass_sm_keep = 0;  // pass 2 only on SMs with smid % mod < keep (0 = everywhere)
   int jpass_ctas_per_sm = 2;
+  int x_cache = 1;        // reuse X = S^-1/2 across nbd_scf_setup calls with a bit-identical overlap matrix
+  int x_valid_n = 0;      // nao the cached S / X belong to (0 = none)
   int jpass_safe = 1;     // 0: pass 2 releases a ring stage before its loads are known to have returned (experiments)
   int syrk_mode = 1;      // 1: the K Gram runs as the stream-K symmetric rank-k kernel (syrk.cuh) when the shape allows
   int syrk_ctas = 0;      // CTAs of that kernel (0 = one per SM)
@@ -192,7 +195,7 @@ struct nbd_ctx {
   int nelec[2] = {0, 0};
   double mu = 0.0;
   DBuf<double> S, Xh, hcore, heff, GS, GSv, F, Huz, vhf, FG, T1, T2, Ct, D, Dold, evals, eigwork, eigwork2, red_part, red_out,
-      Corth, Ssave, dm0f, Fpad;
+      Corth, Ssave, Ssave2, dm0f, Fpad;
   DBuf<int> devinfo;
   DiisState diis;
   // subspace (Chebyshev-filtered) tracking of the occupied block between full eigensolves
@@ -771,20 +774,26 @@ static bool host_is_pageable(const void* p) {
   }
   return a.type == cudaMemoryTypeUnregistered;
 }
+// Copy threads (option "copy_threads"; default: half the host's hardware threads, 2..12).  The destination of a result
+// copy is usually a fresh numpy array: most of the time goes into first-touch page faults, which only parallelise
+// over threads.
+static int g_copy_threads = 0;
 static void parallel_memcpy(char* dst, const char* src, size_t n) {
-  constexpr int T = 4;
-  if (n < (4u << 20)) {
+  constexpr int TMAX = 12;
+  if (g_copy_threads <= 0) g_copy_threads = std::max(2, std::min(TMAX, (int)std::thread::hardware_concurrency() / 2));
+  const int T = std::min(TMAX, g_copy_threads);
+  if (n < (4u << 20) || T < 2) {
     memcpy(dst, src, n);
     return;
   }
-  std::future<void> f[T - 1];
+  std::future<void> f[TMAX - 1];
   const size_t part = (n / T + 63) & ~(size_t)63;
   for (int t = 1; t < T; ++t) {
     const size_t o = std::min(n, part * t), e = std::min(n, part * (t + 1));
     f[t - 1] = std::async(std::launch::async, [=] { memcpy(dst + o, src + o, e - o); });
   }
   memcpy(dst, src, std::min(n, part));
-  for (auto& x : f) x.get();
+  for (int t = 1; t < T; ++t) f[t - 1].get();
 }
 static void staged_copy(nbd_ctx* c, char* host, char* dev, size_t bytes, bool to_host) {
   char* st = (char*)c->pinned.ensure(2 * STAGE_CHUNK);
@@ -919,6 +928,8 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "syrk") c->syrk_mode = (int)value;
   else if (k == "pair_split") c->pair_split = (int)value;
   else if (k == "jpass_safe") c->jpass_safe = (int)value;
+  else if (k == "copy_threads") g_copy_threads = (int)value;
+  else if (k == "x_cache") { if (c->x_cache != (int)value) c->x_valid_n = 0; c->x_cache = (int)value; }
   else if (k == "jpass_sm_mod") c->jpass_sm_mod = (int)value;
   else if (k == "jpass_sm_keep") c->jpass_sm_keep = (int)value;
   else if (k == "jpass_ctas_per_sm") c->jpass_ctas_per_sm = (int)value;

@@ -276,26 +276,42 @@ extern "C" int nbd_scf_setup(nbd_ctx* c, int nspin, const int* nelec, const doub
     for (DBuf<double>* b : {&c->heff, &c->GS, &c->F, &c->Huz, &c->vhf, &c->FG, &c->T1, &c->T2, &c->Ct, &c->D, &c->Dold, &c->Corth})
       b->ensure((size_t)2 * nn);
     c->evals.ensure((size_t)8 * n);
-    h2d(c, c->S.p, ovlp, nn);
+    // The same molecule is embedded several times (DFT-in-DFT and HF-in-DFT, both projectors: nbed/driver.py:1138-1231):
+    // when the uploaded overlap matrix is bit-identical to the one X = S^-1/2 was last built from, X is reused and the
+    // eigendecomposition (17.6 ms at n = 1376) is skipped.  Option "x_cache" = 0 switches the reuse off.
+    bool reuse_x = false;
+    if (c->x_cache && c->x_valid_n == n) {
+      h2d(c, c->FG.p, ovlp, nn);
+      double* out = c->red_out.ensure(64);
+      reduce_to(c, c->FG.p, c->S.p, nn, 1, n, out + 48);
+      double diff = 1.0;
+      d2h(c, &diff, out + 48, 1);
+      NBD_CUDA(cudaStreamSynchronize(c->stream));
+      reuse_x = diff == 0.0;
+    }
+    c->x_valid_n = 0;
+    if (!reuse_x) h2d(c, c->S.p, ovlp, nn);
     h2d(c, c->hcore.p, hcore, nn);
     h2d(c, c->T1.p, v_emb, (size_t)nspin * nn);   // V_emb
     h2d(c, c->T2.p, dm_env, (size_t)nspin * nn);  // gamma_env
-    // X = S^-1/2 = (w^-1/4 V)^T (w^-1/4 V)     (huzinaga_scf.py:128)
-    NBD_CUDA(cudaMemcpyAsync(c->FG.p, c->S.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, c->stream));
-    eigh_batched(c, c->FG.p, c->evals.p, n, 1);
-    {
-      std::vector<double> w(n);
-      d2h(c, w.data(), c->evals.p, n);
-      check_devinfo(c, 1, "overlap eigendecomposition");
-      NBD_REQUIRE(w[0] > 0.0, NBD_ERR_ARG, "overlap matrix is not positive definite (lowest eigenvalue %g)", w[0]);
+    if (!reuse_x) {
+      // X = S^-1/2 = (w^-1/4 V)^T (w^-1/4 V)     (huzinaga_scf.py:128)
+      NBD_CUDA(cudaMemcpyAsync(c->FG.p, c->S.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, c->stream));
+      eigh_batched(c, c->FG.p, c->evals.p, n, 1);
+      {
+        std::vector<double> w(n);
+        d2h(c, w.data(), c->evals.p, n);
+        check_devinfo(c, 1, "overlap eigendecomposition");
+        NBD_REQUIRE(w[0] > 0.0, NBD_ERR_ARG, "overlap matrix is not positive definite (lowest eigenvalue %g)", w[0]);
+      }
+      {
+        dim3 g((n + 127) / 128, n);
+        scale_rows_kernel<<<g, 128, 0, c->stream>>>(c->FG.p, c->evals.p, n, 2);
+        LAUNCH_CHECK(c);
+      }
+      gemm_tn(c, n, n, n, c->FG.p, n, c->FG.p, n, c->Xh.p, n, 1.0, 0.0, 1, 0, 0, 0, /*lower=*/1);
+      symmetrize_lower(c, c->Xh.p, n, 1);
     }
-    {
-      dim3 g((n + 127) / 128, n);
-      scale_rows_kernel<<<g, 128, 0, c->stream>>>(c->FG.p, c->evals.p, n, 2);
-      LAUNCH_CHECK(c);
-    }
-    gemm_tn(c, n, n, n, c->FG.p, n, c->FG.p, n, c->Xh.p, n, 1.0, 0.0, 1, 0, 0, 0, /*lower=*/1);
-    symmetrize_lower(c, c->Xh.p, n, 1);
     // gamma S (huzinaga_scf.py:132)
     gemm_nn(c, n, n, n, c->T2.p, n, c->S.p, n, c->GS.p, n, 1.0, 0.0, nspin, nn, 0, nn);
     if (projector == NBD_MU_SHIFT) {
@@ -314,6 +330,7 @@ extern "C" int nbd_scf_setup(nbd_ctx* c, int nspin, const int* nelec, const doub
     c->sub_bounds_valid = false;
     c->last_eig_full = true;
     finish_call(c);
+    c->x_valid_n = n;  // S and X of this problem are complete on the device
   });
 }
 
@@ -589,14 +606,40 @@ static void mu_eig(nbd_ctx* c, const double* Fsrc, double* Crows) {
   NBD_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 8, c->stream));
   NBD_CUDA(cudaMemcpyAsync(Crows, Fsrc, sizeof(double) * nn * c->nspin, cudaMemcpyDeviceToDevice, c->stream));
   const bool dist = eig_distributed(c, c->nspin);
+  // single rank, two spins: the second solve is issued from a helper thread on the side stream (as in eigh_batched:
+  // the library call blocks its calling thread on internal synchronisations)
+  const bool two_threads = !dist && c->nspin == 2 && c->overlap && c->eig_threads && n >= 512;
   {
     StageScope ts(c->timers, c->stream, "eigh");
+    std::future<cusolverStatus_t> side;
+    if (two_threads) {
+      double* work2 = c->eigwork2.ensure((size_t)lwork);
+      double* sv2 = c->Ssave2.ensure(nn);
+      NBD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+      NBD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+      NBD_CUDA(cudaMemcpyAsync(sv2, c->S.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, c->stream2));
+      const int dev_id = c->device;
+      cusolverDnHandle_t h2 = c->solver2;
+      double* A2 = Crows + nn;
+      double* w2 = c->evals.p + n;
+      side = std::async(std::launch::async, [=] {
+        cudaSetDevice(dev_id);
+        return cusolverDnDsygvd(h2, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A2, n, sv2, n, w2, work2,
+                                lwork, info + 1);
+      });
+    }
     for (int s = 0; s < c->nspin; ++s) {
-      if (dist && s != c->rank) continue;
+      if ((dist && s != c->rank) || (two_threads && s == 1)) continue;
       // scipy.linalg.eigh(f, s): dsygvd overwrites the overlap with its Cholesky factor -> work on a copy
       NBD_CUDA(cudaMemcpyAsync(sv, c->S.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, c->stream));
       NBD_SOLVER(cusolverDnDsygvd(c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n,
                                   Crows + s * nn, n, sv, n, c->evals.p + (long)s * n, work, lwork, info + s));
+    }
+    if (two_threads) {
+      const cusolverStatus_t st2 = side.get();
+      NBD_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+      NBD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+      if (st2 != CUSOLVER_STATUS_SUCCESS) fail(NBD_ERR_CUDA, "cusolverDnDsygvd (side stream): status %d", (int)st2);
     }
   }
   if (dist) eig_exchange(c, Crows, c->evals.p, n);

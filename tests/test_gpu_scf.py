@@ -390,3 +390,36 @@ def test_cluster_split_k_block_product_matches_the_single_cta_kernel(ctx, n, noc
     mf = ps.DFUHF(p.ovlp, p.hcore, p.cderi(), p.nelec, max_cycle=30, conv_tol=1e-8)
     _, e0, d0, _, conv0 = nr.huzinaga_scf(mf, p.v_emb, p.dm_enviro)
     assert a[4]["converged"] == conv0 and np.abs(a[2] - d0).max() < 1e-8
+
+
+def test_overlap_cache_reuses_and_refreshes_x(ctx):
+    """nbd_scf_setup keeps X = S^-1/2 when the uploaded overlap is bit-identical to the previous one (the driver embeds
+    the same molecule several times, nbed/driver.py:1138-1231) and rebuilds it as soon as one element differs."""
+    pa, ba = _problem("C2_h2o_ccpvdz", 3.0)
+    ctx.load_cderi(ba)
+
+    def run(ovlp, cache):
+        ctx.set_option("x_cache", cache)
+        ctx.scf_setup(pa.nelec, ovlp, pa.hcore, pa.v_emb, pa.dm_enviro, NBD_HUZINAGA)
+        ms = ctx.timer_ms("eigh")
+        c, e, d, h, info = ctx.huzinaga_scf(30, 1e-8, 1e-6, True)
+        return e, d, info["trace"].copy(), ms
+
+    try:
+        e0, d0, t0, ms0 = run(pa.ovlp, 0)          # no cache: reference result
+        e1, d1, t1, ms1 = run(pa.ovlp, 1)          # fills the cache (x_cache was just switched: rebuilt)
+        e2, d2, t2, ms2 = run(pa.ovlp, 1)          # reuses X
+        assert ms1 > 0.0 and ms2 <= 0.0, (ms1, ms2)
+        assert np.array_equal(d1, d0) and np.array_equal(d2, d0) and np.array_equal(t2, t0) and np.array_equal(e2, e0)
+        s2 = pa.ovlp.copy()
+        s2[0, 1] += 1e-3
+        s2[1, 0] += 1e-3
+        e3, d3, t3, ms3 = run(s2, 1)               # one element differs: rebuilt
+        assert ms3 > 0.0
+        e4, d4, t4, ms4 = run(s2, 0)
+        assert np.array_equal(d3, d4) and np.array_equal(e3, e4)
+        assert np.abs(d3 - d0).max() > 1e-6
+        e5, d5, t5, ms5 = run(pa.ovlp, 1)          # back to the first overlap: rebuilt again, same result as before
+        assert ms5 > 0.0 and np.array_equal(d5, d0)
+    finally:
+        ctx.set_option("x_cache", 1)
