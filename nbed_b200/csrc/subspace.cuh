@@ -284,6 +284,12 @@ __global__ void __launch_bounds__(128) sub_apply2_kernel(SubApplyArgs a) {
   cluster_sync_all();  // the peers' shared memory stays alive until rank 0 has read it
 }
 
+// (A persistent variant that walked a whole Chebyshev filter in one cooperative launch - grid barrier on a monotonic
+// counter between the steps - was built and measured in round 2: bit-identical results, half the launches, the same
+// time (0.840 against 0.849 ms per cycle at C4).  A block product moves 45 MB through L2 -> SM, ~5.6 us at the measured
+// 8 TB/s, so launch latency was never the limiter; removed again, profiles/r02_persistent_filter.md.)
+constexpr int SUBF_MAX_STEPS = 26;  // filter steps whose coefficients the host precomputes
+
 // G[b][0] = Y^T Y, G[b][1] = Y^T W  (KB x KB each), rows split over gridDim.x CTAs, deterministic final sum.
 template <int KB>
 __global__ void __launch_bounds__(256) sub_gram_kernel(const double* __restrict__ Yall, const double* __restrict__ Wall,

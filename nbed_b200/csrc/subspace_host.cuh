@@ -239,7 +239,7 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
   for (int outer = 0; outer < max_outer; ++outer) {
     if (outer > 0) {
       // scaled Chebyshev filter of degree `degree` damping [a, bound] (Zhou & Saad), per spin
-      double e[2], cc[2], sig[2], sig1[2], al[2], be[2];
+      double e[2], cc[2], sig[2], sig1[2], al[2];
       int degree = max_degree;
       // A tracked block late in the SCF starts close to converged: the residual reduction per filter degree observed
       // earlier in this SCF (c->sub_rate, the slowest seen) tells how many degrees the remaining gap to `tol` needs.
@@ -261,24 +261,22 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
         sig[s] = sig1[s];
         al[s] = sig1[s] / e[s];
       }
-      sub_apply<KB>(c, Fp, c->sV.p, nullptr, c->sY.p, al, cc, zero);
-      double* prev = c->sV.p;
-      double* y = c->sY.p;
-      double* z = c->sZ.p;
-      for (int i = 2; i <= degree; ++i) {
+      // coefficients of all steps (Zhou & Saad's scaled three-term recurrence)
+      double alv[2][SUBF_MAX_STEPS] = {}, bev[2][SUBF_MAX_STEPS] = {};
+      for (int s = 0; s < ns; ++s) alv[s][1] = al[s];
+      for (int i = 2; i <= degree; ++i)
         for (int s = 0; s < ns; ++s) {
           const double sig2 = 1.0 / (2.0 / sig1[s] - sig[s]);
-          al[s] = 2.0 * sig2 / e[s];
-          be[s] = sig[s] * sig2;
+          alv[s][i] = 2.0 * sig2 / e[s];
+          bev[s][i] = sig[s] * sig2;
           sig[s] = sig2;
         }
-        sub_apply<KB>(c, Fp, y, prev, z, al, cc, be);
-        double* t = prev;
-        prev = y;
-        y = z;
-        z = t;
+      double* const bufs[3] = {c->sV.p, c->sY.p, c->sZ.p};
+      cur = bufs[degree % 3];
+      for (int i = 1; i <= degree; ++i) {
+        double ai[2] = {alv[0][i], alv[1][i]}, bi[2] = {bev[0][i], bev[1][i]};
+        sub_apply<KB>(c, Fp, bufs[(i - 1) % 3], i >= 2 ? bufs[(i - 2) % 3] : nullptr, bufs[i % 3], ai, cc, i >= 2 ? bi : zero);
       }
-      cur = y;
     }
     // W = F' Y ; G = Y^T Y, H = Y^T W ; host Rayleigh-Ritz ; V = Y M, AV = W M, residuals
     sub_apply<KB>(c, Fp, cur, nullptr, c->sW.p, one, zero, zero);
