@@ -206,7 +206,8 @@ struct nbd_ctx {
   int sub_kb = 0;
   long sub_applies = 0, sub_fallbacks = 0, sub_outer = 0, sub_lanczos = 0, sub_cold_starts = 0;
   double sub_theta[2][32];
-  DBuf<double> sV, sY, sZ, sW, sAV, sPart, sG, sGpart, sM, sTheta, sRpart, sBound, sFprev, sLz;
+  DBuf<double> sV, sY, sZ, sW, sAV, sPart, sG, sGpart, sM, sTheta, sRpart, sBound, sFprev, sLz, sXchg;
+  int dist_sub = 1;  // >= 2 ranks, two spins: ranks 0 / 1 track one spin's eigenvector block each, blocks are broadcast
   // spectral bounds of the filter: 0 = Gershgorin every cycle; 1 = Lanczos once, then widened by ||F'_k - F'_{k-1}||_F
   int sub_bound_mode = 1;
   int sub_adaptive = 1;   // filter degree of a tracked block from the observed residual reduction per degree
@@ -939,6 +940,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "sub_cold") c->sub_cold = (int)value;
   else if (k == "sub_apply_variant") c->sub_apply_variant = (int)value;
   else if (k == "sub_adaptive") c->sub_adaptive = (int)value;
+  else if (k == "dist_sub") c->dist_sub = (int)value;
   else if (k == "sub_min_nao") { c->sub_min_nao = (int)value; c->sub_valid = false; }
   else return NBD_ERR_ARG;
   return NBD_OK;

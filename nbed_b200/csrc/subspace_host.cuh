@@ -46,8 +46,9 @@ static void sub_init_from_full(nbd_ctx* c, const double* eigrows, const double* 
 }
 
 // k-step Lanczos per spin (batched): up = theta_max + beta_k (+ 2 % of the Ritz spread), low = theta_min - beta_k.
-static void sub_lanczos_bounds(nbd_ctx* c, const double* Fp, double* up, double* low) {
-  const int n = c->nao, ns = c->nspin;
+// Spins [s0, s0 + ns) of the problem; Fp, up, low are indexed by the LOCAL spin 0 .. ns-1 (the caller offsets them).
+static void sub_lanczos_bounds(nbd_ctx* c, const double* Fp, double* up, double* low, int s0, int ns) {
+  const int n = c->nao;
   const int steps = std::min(10, n);
   const int nblk = (n + 7) / 8;
   double* buf = c->sLz.ensure((size_t)3 * ns * n + (size_t)2 * ns * nblk);
@@ -57,7 +58,7 @@ static void sub_lanczos_bounds(nbd_ctx* c, const double* Fp, double* up, double*
   for (int s = 0; s < ns; ++s) {
     double nrm = 0.0;
     for (int i = 0; i < n; ++i) {
-      unsigned long long z = (unsigned long long)(s * n + i) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+      unsigned long long z = (unsigned long long)((s0 + s) * n + i) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
       z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
       z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
       z = z ^ (z >> 31);
@@ -109,8 +110,8 @@ static void sub_lanczos_bounds(nbd_ctx* c, const double* Fp, double* up, double*
 // Interval [low, up] containing the spectrum of Fp (per spin) for the Chebyshev filter.  Mode 1: the bounds of the
 // last matrix widened by the Frobenius norm of the change (rigorous: |lambda(A + E) - lambda(A)| <= ||E||_2 <= ||E||_F),
 // refreshed by a new Lanczos run whenever they have drifted by a quarter of the width.  Mode 0: row-sum bound.
-static void sub_spectral_bounds(nbd_ctx* c, const double* Fp, double* up, double* low) {
-  const int n = c->nao, ns = c->nspin;
+static void sub_spectral_bounds(nbd_ctx* c, const double* Fp, double* up, double* low, int s0, int ns) {
+  const int n = c->nao;
   const long nn = (long)n * n;
   if (c->sub_bound_mode == 0) {
     const int nblk = (n + 7) / 8;
@@ -128,7 +129,7 @@ static void sub_spectral_bounds(nbd_ctx* c, const double* Fp, double* up, double
     return;
   }
   constexpr int NBLK = 64;
-  double* prev = c->sFprev.ensure((size_t)ns * nn);
+  double* prev = c->sFprev.ensure((size_t)c->nspin * nn) + (long)s0 * nn;
   bool refresh = !c->sub_bounds_valid;
   if (!refresh) {
     double* bp = c->sBound.ensure((size_t)2 * NBLK);
@@ -141,21 +142,21 @@ static void sub_spectral_bounds(nbd_ctx* c, const double* Fp, double* up, double
       double d2 = 0.0;
       for (int k = 0; k < NBLK; ++k) d2 += hb[(size_t)s * NBLK + k];
       const double d = std::sqrt(d2) * (1.0 + 1e-12);
-      up[s] = c->sub_up[s] + d;
-      low[s] = c->sub_low[s] - d;
-      if (!(up[s] - c->sub_up_ref[s] <= 0.25 * (c->sub_up_ref[s] - c->sub_low_ref[s]))) refresh = true;
+      up[s] = c->sub_up[s0 + s] + d;
+      low[s] = c->sub_low[s0 + s] - d;
+      if (!(up[s] - c->sub_up_ref[s0 + s] <= 0.25 * (c->sub_up_ref[s0 + s] - c->sub_low_ref[s0 + s]))) refresh = true;
     }
   }
   if (refresh) {
-    sub_lanczos_bounds(c, Fp, up, low);
+    sub_lanczos_bounds(c, Fp, up, low, s0, ns);
     for (int s = 0; s < ns; ++s) {
-      c->sub_up_ref[s] = up[s];
-      c->sub_low_ref[s] = low[s];
+      c->sub_up_ref[s0 + s] = up[s];
+      c->sub_low_ref[s0 + s] = low[s];
     }
   }
   for (int s = 0; s < ns; ++s) {
-    c->sub_up[s] = up[s];
-    c->sub_low[s] = low[s];
+    c->sub_up[s0 + s] = up[s];
+    c->sub_low[s0 + s] = low[s];
   }
   NBD_CUDA(cudaMemcpyAsync(prev, Fp, sizeof(double) * ns * nn, cudaMemcpyDeviceToDevice, c->stream));
   c->sub_bounds_valid = true;
@@ -178,14 +179,15 @@ static void sub_init_cold(nbd_ctx* c) {
 
 template <int KB>
 static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double* Z, double* out, const double* alpha,
-                      const double* shift, const double* beta) {
+                      const double* shift, const double* beta, int ns) {
   const int n = c->nao;
   SubApplyArgs a{};
   a.A = A; a.Y = Y; a.Z = Z; a.out = out;
   a.n = n;
   const int nrb = (n + SUB_ROWS - 1) / SUB_ROWS;
   for (int b = 0; b < 2; ++b) {
-    a.alpha[b] = alpha[b]; a.shift[b] = shift[b]; a.beta[b] = beta[b];
+    const int q = b < ns ? b : 0;
+    a.alpha[b] = alpha[q]; a.shift[b] = shift[q]; a.beta[b] = beta[q];
   }
   if (c->sub_apply_variant == 0) {
     // cluster split-K kernel: 32 rows per CTA, 4 CTAs of a cluster share the contraction index, DSMEM reduction
@@ -194,7 +196,7 @@ static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double
     if (first_use_on_current_device(configured2))
       NBD_CUDA(cudaFuncSetAttribute(sub_apply2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((n + SUB2_ROWS - 1) / SUB2_ROWS, SUB2_KS, c->nspin);
+    cfg.gridDim = dim3((n + SUB2_ROWS - 1) / SUB2_ROWS, SUB2_KS, ns);
     cfg.blockDim = dim3(128);
     cfg.dynamicSmemBytes = smem2;
     cfg.stream = c->stream;
@@ -210,7 +212,7 @@ static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double
     ++c->sub_applies;
     return;
   }
-  dim3 g(nrb, 1, c->nspin);
+  dim3 g(nrb, 1, ns);
   constexpr int smem = sub_apply_smem_bytes<KB>();
   static unsigned long long configured = 0;
   if (first_use_on_current_device(configured)) NBD_CUDA(cudaFuncSetAttribute(sub_apply_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -219,27 +221,34 @@ static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double
   ++c->sub_applies;
 }
 
-// Tracks the KB lowest eigenvectors of Fp ([nspin][n][n], Lowdin basis) starting from c->sV.
+// Tracks the KB lowest eigenvectors of spins [s0, s0 + ns) of Fp ([nspin][n][n], Lowdin basis) starting from c->sV.
 // On success c->sV holds the Ritz vectors, c->sub_theta the Ritz values; returns false when it did not converge.
 template <int KB>
-static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
-  const int n = c->nao, ns = c->nspin;
-  const long blk = (long)n * KB;
+static bool sub_solve_t(nbd_ctx* c, const double* Fp_all, int s0, int ns) {
+  const int n = c->nao;
+  const long blk = (long)n * KB, nn = (long)n * n;
   constexpr int NBLK = 64;
   const bool cold = c->sub_is_cold;
   c->sub_is_cold = false;
   const int max_degree = 24, max_outer = cold ? 24 : 14;
   const double tol = 1e-10;
+  // device views of the spins handled here
+  const double* Fp = Fp_all + (long)s0 * nn;
+  double *sV = c->sV.p + s0 * blk, *sY = c->sY.p + s0 * blk, *sZ = c->sZ.p + s0 * blk, *sW = c->sW.p + s0 * blk,
+         *sAV = c->sAV.p + s0 * blk;
+  double *sG = c->sG.p + (long)s0 * 2 * KB * KB, *sGpart = c->sGpart.p + (long)s0 * NBLK * 2 * KB * KB,
+         *sM = c->sM.p + (long)s0 * KB * KB, *sTheta = c->sTheta.p + (long)s0 * KB, *sRpart = c->sRpart.p + (long)s0 * NBLK * KB;
+  unsigned int* ticket = c->sTicket.p + 2048 + s0;
   double bound[2] = {0, 0}, lowb[2] = {0, 0}, bu_used[2] = {0, 0};
-  sub_spectral_bounds(c, Fp, bound, lowb);
+  sub_spectral_bounds(c, Fp, bound, lowb, s0, ns);
   const double one[2] = {1.0, 1.0}, zero[2] = {0.0, 0.0};
-  double* cur = c->sV.p;  // block to Rayleigh-Ritz next
+  double* cur = sV;  // block to Rayleigh-Ritz next
   double worst_prev = -1.0;
   int deg_prev = 0;
   for (int outer = 0; outer < max_outer; ++outer) {
     if (outer > 0) {
       // scaled Chebyshev filter of degree `degree` damping [a, bound] (Zhou & Saad), per spin
-      double e[2], cc[2], sig[2], sig1[2], al[2];
+      double e[2], cc[2] = {0, 0}, sig[2], sig1[2], al[2];
       int degree = max_degree;
       // A tracked block late in the SCF starts close to converged: the residual reduction per filter degree observed
       // earlier in this SCF (c->sub_rate, the slowest seen) tells how many degrees the remaining gap to `tol` needs.
@@ -248,7 +257,7 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
         if (need < max_degree) degree = std::max(6, (int)std::ceil(need) + 2);
       }
       for (int s = 0; s < ns; ++s) {
-        const double a = c->sub_theta[s][KB - 1], a0 = c->sub_theta[s][0];
+        const double a = c->sub_theta[s0 + s][KB - 1], a0 = c->sub_theta[s0 + s][0];
         const double bu = std::max(bound[s], a + 1e-3) + 1e-7 * std::fabs(bound[s]) + 1e-9;
         bu_used[s] = bu;
         // mode 0 has no estimate of the lowest eigenvalue: tracked blocks (theta_0 converged) take the full degree
@@ -271,19 +280,19 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
           bev[s][i] = sig[s] * sig2;
           sig[s] = sig2;
         }
-      double* const bufs[3] = {c->sV.p, c->sY.p, c->sZ.p};
+      double* const bufs[3] = {sV, sY, sZ};
       cur = bufs[degree % 3];
       for (int i = 1; i <= degree; ++i) {
         double ai[2] = {alv[0][i], alv[1][i]}, bi[2] = {bev[0][i], bev[1][i]};
-        sub_apply<KB>(c, Fp, bufs[(i - 1) % 3], i >= 2 ? bufs[(i - 2) % 3] : nullptr, bufs[i % 3], ai, cc, i >= 2 ? bi : zero);
+        sub_apply<KB>(c, Fp, bufs[(i - 1) % 3], i >= 2 ? bufs[(i - 2) % 3] : nullptr, bufs[i % 3], ai, cc, i >= 2 ? bi : zero, ns);
       }
     }
     // W = F' Y ; G = Y^T Y, H = Y^T W ; host Rayleigh-Ritz ; V = Y M, AV = W M, residuals
-    sub_apply<KB>(c, Fp, cur, nullptr, c->sW.p, one, zero, zero);
-    sub_gram_kernel<KB><<<dim3(NBLK, ns), 256, 0, c->stream>>>(cur, c->sW.p, c->sGpart.p, c->sG.p, c->sTicket.p + 2048, n);
+    sub_apply<KB>(c, Fp, cur, nullptr, sW, one, zero, zero, ns);
+    sub_gram_kernel<KB><<<dim3(NBLK, ns), 256, 0, c->stream>>>(cur, sW, sGpart, sG, ticket, n);
     LAUNCH_CHECK(c);
     std::vector<double> G((size_t)ns * 2 * KB * KB), M((size_t)ns * KB * KB), th((size_t)ns * KB);
-    d2h(c, G.data(), c->sG.p, G.size());
+    d2h(c, G.data(), sG, G.size());
     NBD_CUDA(cudaStreamSynchronize(c->stream));
     for (int s = 0; s < ns; ++s)
       if (!sub_rayleigh_ritz(KB, G.data() + (size_t)s * 2 * KB * KB, G.data() + (size_t)s * 2 * KB * KB + KB * KB,
@@ -295,20 +304,20 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
         c->sub_bounds_valid = false;
         return false;
       }
-    h2d(c, c->sM.p, M.data(), M.size());
-    h2d(c, c->sTheta.p, th.data(), th.size());
+    h2d(c, sM, M.data(), M.size());
+    h2d(c, sTheta, th.data(), th.size());
     // rotate into a buffer that is not `cur` (cur may alias sV / sY / sZ): use sAV for A V and the free one for V
-    double* vout = (cur == c->sV.p) ? c->sY.p : c->sV.p;
-    sub_rotate_kernel<KB><<<dim3(NBLK, ns), 256, 0, c->stream>>>(cur, c->sW.p, c->sM.p, c->sTheta.p, vout, c->sAV.p, c->sRpart.p, n);
+    double* vout = (cur == sV) ? sY : sV;
+    sub_rotate_kernel<KB><<<dim3(NBLK, ns), 256, 0, c->stream>>>(cur, sW, sM, sTheta, vout, sAV, sRpart, n);
     LAUNCH_CHECK(c);
-    if (vout != c->sV.p) NBD_CUDA(cudaMemcpyAsync(c->sV.p, vout, sizeof(double) * blk * ns, cudaMemcpyDeviceToDevice, c->stream));
+    if (vout != sV) NBD_CUDA(cudaMemcpyAsync(sV, vout, sizeof(double) * blk * ns, cudaMemcpyDeviceToDevice, c->stream));
     std::vector<double> rp((size_t)ns * NBLK * KB);
-    d2h(c, rp.data(), c->sRpart.p, rp.size());
+    d2h(c, rp.data(), sRpart, rp.size());
     NBD_CUDA(cudaStreamSynchronize(c->stream));
     double worst = 0.0;
     for (int s = 0; s < ns; ++s) {
-      const int o = ns == 2 ? c->nelec[s] : (c->nelec[0] + c->nelec[1]) / 2;
-      for (int k = 0; k < KB; ++k) c->sub_theta[s][k] = th[(size_t)s * KB + k];
+      const int o = c->nspin == 2 ? c->nelec[s0 + s] : (c->nelec[0] + c->nelec[1]) / 2;
+      for (int k = 0; k < KB; ++k) c->sub_theta[s0 + s][k] = th[(size_t)s * KB + k];
       for (int k = 0; k < o; ++k) {
         double r2 = 0.0;
         for (int bl = 0; bl < NBLK; ++bl) r2 += rp[((size_t)s * NBLK + bl) * KB + k];
@@ -324,9 +333,48 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp) {
   return false;
 }
 
+// With a communicator of >= 2 ranks and two spins, rank 0 tracks the alpha block and rank 1 the beta block - each block
+// product then moves half the data of the joint one - and the converged blocks (+ Ritz values and a status word) are
+// broadcast, so every rank continues with bit-identical orbitals.  The collectives are issued on every rank whatever
+// the local outcome; a failure on either owner sends all ranks to the library eigensolver together.
+template <int KB>
+static bool sub_solve_split(nbd_ctx* c, const double* Fp) {
+  const int n = c->nao;
+  const long blk = (long)n * KB;
+  bool ok_local = true;
+  if (c->rank < 2) ok_local = sub_solve_t<KB>(c, Fp, c->rank, 1);
+  else c->sub_is_cold = false;
+  StageScope ts(c->timers, c->stream, "eig_bcast");
+  double* x = c->sXchg.ensure((size_t)2 * (KB + 2));
+  if (c->rank < 2) {
+    double hx[KB + 2];
+    for (int k = 0; k < KB; ++k) hx[k] = c->sub_theta[c->rank][k];
+    hx[KB] = ok_local ? 1.0 : 0.0;
+    hx[KB + 1] = c->sub_bounds_valid ? 1.0 : 0.0;
+    h2d(c, x + (long)c->rank * (KB + 2), hx, KB + 2);
+  }
+  ncclResult_t r = g_nccl.GroupStart();
+  for (int s = 0; s < 2 && r == ncclSuccess; ++s) {
+    r = g_nccl.Broadcast(c->sV.p + s * blk, c->sV.p + s * blk, (size_t)blk, ncclDouble, s, c->comm, c->stream);
+    if (r == ncclSuccess) r = g_nccl.Broadcast(x + (long)s * (KB + 2), x + (long)s * (KB + 2), (size_t)(KB + 2), ncclDouble, s, c->comm, c->stream);
+  }
+  if (r == ncclSuccess) r = g_nccl.GroupEnd();
+  if (r != ncclSuccess) fail(NBD_ERR_CUDA, "ncclBroadcast (eigenvector blocks): %s", g_nccl.GetErrorString(r));
+  double hx[2 * (KB + 2)];
+  d2h(c, hx, x, 2 * (KB + 2));
+  NBD_CUDA(cudaStreamSynchronize(c->stream));
+  bool ok = true;
+  for (int s = 0; s < 2; ++s) {
+    for (int k = 0; k < KB; ++k) c->sub_theta[s][k] = hx[s * (KB + 2) + k];
+    ok = ok && hx[s * (KB + 2) + KB] == 1.0;
+  }
+  return ok;
+}
+
 static bool sub_solve(nbd_ctx* c, const double* Fp) {
   StageScope ts(c->timers, c->stream, "eig_sub");
-  if (c->sub_kb == 16) return sub_solve_t<16>(c, Fp);
-  if (c->sub_kb == 32) return sub_solve_t<32>(c, Fp);
+  const bool split = c->world >= 2 && c->comm && c->nspin == 2 && c->dist_sub;
+  if (c->sub_kb == 16) return split ? sub_solve_split<16>(c, Fp) : sub_solve_t<16>(c, Fp, 0, c->nspin);
+  if (c->sub_kb == 32) return split ? sub_solve_split<32>(c, Fp) : sub_solve_t<32>(c, Fp, 0, c->nspin);
   return false;
 }
