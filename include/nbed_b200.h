@@ -111,7 +111,9 @@ int nbd_xc_setup(nbd_ctx* ctx, int xc_code, const int* atm, int natm, const int*
 int nbd_xc_nr_uks(nbd_ctx* ctx, const double* dm, double* nelec, double* exc, double* vxc);
 /* on = 1: nbd_huzinaga_scf / nbd_mu_scf treat the SCF object as UKS: get_veff = J - hyb K + V_xc, the Huzinaga loop
  * uses calculate_ks_energy (ecoul + exc + tr[D (h + Huz + V)]); nbd_mu_scf keeps nbed's patched energy_elec unless
- * option "ks_energy" = 1 (plain pyscf UKS.energy_elec: e1 + ecoul + exc).  Spin-resolved (nspin = 2) only. */
+ * option "ks_energy" = 1 (plain pyscf UKS.energy_elec: e1 + ecoul + exc).  nbd_huzinaga_scf also takes restricted
+ * Kohn-Sham objects (nspin = 1, pyscf/dft/rks.py: J - hyb / 2 K + V_xc[D / 2, D / 2], scalar energy); nbd_mu_scf is
+ * spin-resolved like the reference's mu path. */
 int nbd_scf_set_xc(nbd_ctx* ctx, int on);
 
 /* ---- J/K --------------------------------------------------------------------------------------- */

@@ -32,24 +32,43 @@ static void scf_build_fock(nbd_ctx* c, int Ntot, const std::vector<KGroup>& grou
   const long nn = (long)n * n;
   const int ns = c->nspin;
   const bool ks = c->xc.on;
-  if (ks) NBD_REQUIRE(ns == 2, NBD_ERR_UNSUPPORTED, "the Kohn-Sham branch is spin-resolved (the reference's drivers build UKS objects, driver.py:289-313)");
   double* buf = c->d_jk.ensure((size_t)(1 + ns) * nn);
   std::vector<int> jbegin = {0, Ntot};
   jk_device(c, c->d_orb.p, c->d_wt.p, Ntot, 1, jbegin, buf, ns, groups, buf + nn);
   all_reduce(c, buf, (size_t)(1 + ns) * nn);
   {
     StageScope ts(c->timers, c->stream, "fock");
-    const double kscale = ks ? c->xc.hyb : (ns == 2 ? 1.0 : 0.5);
+    // UHF: J - K_s; RHF: J - K / 2; UKS: J - hyb K_s; RKS: J - hyb K / 2   (pyscf/dft/{uks,rks}.py:get_veff)
+    const double kscale = (ks ? c->xc.hyb : 1.0) * (ns == 2 ? 1.0 : 0.5);
     fock_from_heff_kernel<<<grid1(nn, 256), 256, 0, c->stream>>>(c->heff.p, buf, buf + nn, kscale, c->F.p, c->vhf.p, nn, ns);
     LAUNCH_CHECK(c);
   }
   if (!ks) return;
   double in3[3];
+  double* out = c->red_out.ensure(64);
+  if (ns == 1) {
+    // restricted Kohn-Sham object (pyscf/dft/rks.py:get_veff; the object type of the reference's tests/test_scf.py:19-40):
+    // nr_rks of the total density = nr_uks of the spin-unpolarised pair (D / 2, D / 2) - same energy, V_xc of either spin
+    double* pair = c->dm0f.ensure((size_t)2 * nn);
+    halve_to_pair_kernel<<<grid1(nn, 256), 256, 0, c->stream>>>(c->D.p, pair, nn);
+    LAUNCH_CHECK(c);
+    xc_eval_device(c, pair, in3);
+    StageScope ts(c->timers, c->stream, "fock");
+    xc_add_potential_kernel<<<grid1(nn, 256), 256, 0, c->stream>>>(c->xc.V.p, c->F.p, c->vhf.p, nn);
+    LAUNCH_CHECK(c);
+    reduce_to(c, c->D.p, buf, nn, 0, n, out + 52);       // tr(D J)
+    reduce_to(c, c->D.p, buf + nn, nn, 0, n, out + 53);  // tr(D K)
+    double h[2];
+    d2h(c, h, out + 52, 2);
+    NBD_CUDA(cudaStreamSynchronize(c->stream));
+    c->xc.ecoul = 0.5 * h[0];
+    c->xc.exc = in3[0] - 0.25 * c->xc.hyb * h[1];
+    return;
+  }
   xc_eval_device(c, c->D.p, in3);
   StageScope ts(c->timers, c->stream, "fock");
   xc_add_potential_kernel<<<grid1(2 * nn, 256), 256, 0, c->stream>>>(c->xc.V.p, c->F.p, c->vhf.p, 2 * nn);
   LAUNCH_CHECK(c);
-  double* out = c->red_out.ensure(64);
   reduce_to(c, c->D.p, buf, nn, 0, n, out + 52);             // tr(D_a J)
   reduce_to(c, c->D.p + nn, buf, nn, 0, n, out + 53);        // tr(D_b J)
   reduce_to(c, c->D.p, buf + nn, 2 * nn, 0, n, out + 54);    // sum_s tr(D_s K_s)

@@ -329,6 +329,15 @@ __global__ void sum_partials_kernel(const double* __restrict__ part, int nparts,
   out[e] = s;
 }
 // F_s += V_s, vhf_s += V_s
+// pair[0] = pair[1] = D / 2: the spin densities of a restricted Kohn-Sham object
+__global__ void halve_to_pair_kernel(const double* __restrict__ D, double* __restrict__ pair, long cnt) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) {
+    const double v = 0.5 * D[i];
+    pair[i] = v;
+    pair[cnt + i] = v;
+  }
+}
 __global__ void xc_add_potential_kernel(const double* __restrict__ V, double* __restrict__ F, double* __restrict__ vhf, long cnt) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cnt) return;

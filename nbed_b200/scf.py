@@ -6,7 +6,8 @@ Mirrors (same names, argument meaning and return contract):
 * ``get_huzinaga_operator``   nbed/scf/huzinaga_scf.py:65-90   (device GEMM + fused symmetrise)
 * ``energy_elec``             nbed/scf/embedded_hcore_funcs.py:11-46
 * ``mu_embed``                NbedDriver._mu_embed, nbed/driver.py:500-538 (+ ``_env_projector`` :433-449)
-* ``B200RHF`` / ``B200UHF``   the duck-typed PySCF SCF-object protocol the reference drives:
+* ``B200RHF`` / ``B200UHF`` / ``B200RKS`` / ``B200UKS``   the duck-typed PySCF SCF-object protocol the reference drives
+  (the four object types of the reference's tests/test_scf.py):
   ``get_ovlp, get_hcore, get_veff, get_jk, get_j, get_occ, make_rdm1, energy_elec, energy_tot, energy_nuc,
   get_fock, max_cycle, conv_tol, mo_coeff, mo_occ, mo_energy, e_tot, converged, mol``.
 
@@ -276,6 +277,56 @@ class B200RHF(_B200SCF):
         e_coul = 0.5 * np.einsum("ij,ji->", vhf, dm)
         self.scf_summary["e1"], self.scf_summary["e2"] = e1, e_coul
         return e1 + e_coul, e_coul
+
+
+class B200RKS(B200RHF):
+    """``pyscf.dft.RKS(mol).density_fit()`` analogue (the object type of the reference's ``tests/test_scf.py:19-40``; its
+    drivers build UKS objects).  Rank-2 arrays throughout; ``nr_rks`` of the total density runs as ``nr_uks`` of the
+    spin-unpolarised pair (D / 2, D / 2).  ``grids`` / ``basis`` as for ``B200UKS``."""
+
+    is_ks = True
+    HYB = B200UKS.HYB
+
+    def __init__(self, ctx, ovlp, hcore, nelec, xc="b3lyp", grids=None, basis=None, **kw):
+        super().__init__(ctx, ovlp, hcore, nelec, **kw)
+        if grids is None or basis is None:
+            raise ValueError("B200RKS needs grids = (coords, weights) and basis = (atm, bas, env)")
+        self.xc = str(xc).lower()
+        self.grids, self.basis = grids, basis
+        ctx.xc_setup(self.xc, *basis, *grids)
+
+    def get_veff(self, mol=None, dm=None, dm_last=0, vhf_last=0, hermi=1):
+        """pyscf/dft/rks.py:get_veff: vxc + vj - hyb / 2 vk, tagged with ecoul / exc / vj / vk."""
+        if dm is None:
+            dm = self.make_rdm1()
+        d = np.asarray(dm)
+        _, exc, vxc2 = self.ctx.xc_nr_uks(np.asarray((d * 0.5, d * 0.5)))
+        vxc = vxc2[0]
+        hyb = self.HYB[self.xc]
+        if abs(hyb) < 1e-10:
+            vj = self.get_j(mol, dm, hermi)
+            vxc = vxc + vj
+            vk = None
+        else:
+            vj, vk = self.get_jk(mol, dm, hermi)
+            vk = vk * hyb
+            vxc = vxc + vj - vk * 0.5
+            exc -= np.einsum("ij,ji", d, vk).real * 0.5 * 0.5
+        ecoul = np.einsum("ij,ji", d, vj).real * 0.5
+        return tag_array(vxc, ecoul=float(ecoul), exc=float(exc), vj=vj, vk=vk)
+
+    def energy_elec(self, dm=None, h1e=None, vhf=None):
+        """pyscf/dft/rks.py:energy_elec: e1 + ecoul + exc."""
+        if dm is None:
+            dm = self.make_rdm1()
+        if h1e is None:
+            h1e = self.get_hcore()
+        if vhf is None or getattr(vhf, "ecoul", None) is None:
+            vhf = self.get_veff(dm=dm)
+        e1 = np.einsum("ij,ji->", np.asarray(h1e), np.asarray(dm)).real
+        e2 = vhf.ecoul + vhf.exc
+        self.scf_summary.update(e1=float(e1), coul=vhf.ecoul, exc=vhf.exc)
+        return float(e1 + e2), float(e2)
 
 
 # ---- nbed/scf/embedded_hcore_funcs.py:11-46 -----------------------------------------------------------

@@ -40,8 +40,8 @@ class _UHF(ps.DFUHF, StreamObject):
     pass
 
 
-class _RKS(StreamObject):
-    pass
+class _RKS(xcr.DFRKS, StreamObject):
+    """Stands in for pyscf.dft.rks.RKS (the object type of the reference's tests/test_scf.py:19-40)."""
 
 
 class _UKS(xcr.DFUKS, StreamObject):
@@ -113,5 +113,5 @@ def install():
 
 def make_scf(kind: str, ovlp, hcore, cderi, nelec, **kw):
     """A stub-typed SCF object that passes the reference's ``isinstance`` checks (huzinaga_scf.py:176,181)."""
-    cls = {"rhf": _RHF, "uhf": _UHF, "uks": _UKS}[kind]
+    cls = {"rhf": _RHF, "uhf": _UHF, "uks": _UKS, "rks": _RKS}[kind]
     return cls(ovlp, hcore, cderi, nelec, **kw)

@@ -359,3 +359,51 @@ class DFUKS(ps.DFUHF):
         e2 = vhf.ecoul + vhf.exc
         self.scf_summary.update(e1=e1, coul=vhf.ecoul, exc=vhf.exc)
         return e1 + e2, e2
+
+
+class DFRKS(ps.DFRHF):
+    """Duck-typed ``pyscf.dft.RKS(...).density_fit()`` on explicit tensors and an explicit grid (the object type of the
+    reference's ``tests/test_scf.py:19-40``; its drivers only build UKS objects, nbed/driver.py:289-313)."""
+
+    is_ks = True
+
+    def __init__(self, ovlp, hcore, cderi, nelec, ao, weights, xc="b3lyp", **kw):
+        super().__init__(ovlp, hcore, cderi, nelec, **kw)
+        self.ao, self.weights, self.xc = ao, weights, xc
+        self.n_xc_builds = 0
+
+    def get_veff(self, mol=None, dm=None, dm_last=0, vhf_last=0, hermi=1):
+        """pyscf/dft/rks.py:get_veff: vxc + vj - hyb / 2 vk on the total density, tagged ecoul / exc / vj / vk.
+        ``nr_rks`` is ``nr_uks`` on the spin-unpolarised pair (dm / 2, dm / 2): same energy, vxc of either spin."""
+        if dm is None:
+            dm = self.make_rdm1()
+        dm = np.asarray(dm)
+        self.n_xc_builds += 1
+        _, exc, vxc2 = nr_uks(self.xc, self.ao, self.weights, np.asarray((dm * 0.5, dm * 0.5)))
+        vxc = vxc2[0]
+        hyb = HYB[self.xc]
+        if abs(hyb) < 1e-10:
+            vj = self.get_j(mol, dm, hermi)
+            vxc = vxc + vj
+            vk = None
+        else:
+            vj, vk = self.get_jk(mol, dm, hermi)
+            vk = vk * hyb
+            vxc = vxc + vj - vk * 0.5
+            exc -= np.einsum("ij,ji", dm, vk).real * 0.5 * 0.5
+        ecoul = np.einsum("ij,ji", dm, vj).real * 0.5
+        return ps.tag_array(vxc, ecoul=ecoul, exc=exc, vj=vj, vk=vk)
+
+    def energy_elec(self, dm=None, h1e=None, vhf=None):
+        """pyscf/dft/rks.py:energy_elec: e1 + ecoul + exc."""
+        if dm is None:
+            dm = self.make_rdm1()
+        if h1e is None:
+            h1e = self.get_hcore()
+        if vhf is None or getattr(vhf, "ecoul", None) is None:
+            vhf = self.get_veff(dm=dm)
+        e1 = np.einsum("ij,ji->", np.asarray(h1e), np.asarray(dm)).real
+        e2 = vhf.ecoul + vhf.exc
+        self.scf_summary.update(e1=e1, coul=vhf.ecoul, exc=vhf.exc)
+        return e1 + e2, e2
+

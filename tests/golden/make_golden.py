@@ -136,10 +136,18 @@ def reference_runs_ks():
     act = stubs.make_scf("uks", p["s"], p["h"], p["cderi"], (4, 4), ao=p["ao"], weights=p["weights"], xc="b3lyp",
                          max_cycle=40, conv_tol=1e-9)
     c, e, d, hz, conv = huzinaga_scf(act, p["v_emb"], p["dm_env"], dm_conv_tol=1e-7)
+    # the same embedding driven through a restricted Kohn-Sham object (rank-2 arrays, doubled environment density:
+    # occupied/base.py:84-85), the object type of the reference's tests/test_scf.py:19-40
+    rks = stubs.make_scf("rks", p["s"], p["h"], p["cderi"], (4, 4), ao=p["ao"], weights=p["weights"], xc="b3lyp",
+                         max_cycle=40, conv_tol=1e-9)
+    from nbed.scf.huzinaga_scf import calculate_ks_energy  # (nbed.scf.huzinaga_scf the attribute is the function)
+    cr, er, dr, hzr, convr = huzinaga_scf(rks, p["v_emb"][0], 2.0 * p["dm_env"][0], dm_conv_tol=1e-7)
+    out_rks = dict(rks_e=er, rks_dm=np.asarray(dr), rks_huz=hzr, rks_conv=convr, rks_n_veff=rks.n_xc_builds,
+                   rks_energy=float(calculate_ks_energy(rks, p["v_emb"][0], dr, hzr)))
     out = dict(global_e_tot=p["global_e_tot"], global_energy_elec=np.array(p["global_ks"].energy_elec()),
                ref_global_e_tot=-75.3091447400438, ref_global_energy_elec=np.array([-84.59485896172163, 37.93302591280513]),
                v_emb=p["v_emb"], c_env=p["c_env"], ks_e=e, ks_dm=np.asarray(d), ks_huz=hz, ks_conv=conv,
-               ks_n_veff=act.n_xc_builds, ngrid=len(p["weights"]))
+               ks_n_veff=act.n_xc_builds, ngrid=len(p["weights"]), **out_rks)
     np.savez_compressed(os.path.join(HERE, "reference_runs_ks.npz"), **out)
     return out
 

@@ -229,6 +229,23 @@ def test_ks_branch_restatement_matches_the_unmodified_reference():
     assert np.abs(np.asarray(d) + p["dm_env"] - np.asarray(p["global_ks"].make_rdm1())).max() < 1e-6
 
 
+def test_rks_branch_restatement_matches_the_unmodified_reference():
+    """The same embedding through a RESTRICTED Kohn-Sham object (rank-2 arrays, doubled environment density; the object
+    type of the reference's tests/test_scf.py:19-40): oracle DFRKS under the restated loop against the fixture written
+    by the unmodified reference loop over the stub RKS object, incl. the scalar calculate_ks_energy of the result."""
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_runs_ks.npz"))
+    p = _ks_problem()
+    act = xcr.DFRKS(p["s"], p["h"], p["cderi"], (4, 4), p["ao"], p["weights"], "b3lyp", max_cycle=40, conv_tol=1e-9)
+    tr = []
+    c, e, d, hz, conv = nr.huzinaga_scf(act, p["v_emb"][0], 2.0 * p["dm_env"][0], dm_conv_tol=1e-7, trace=tr)
+    assert conv == bool(fx["rks_conv"]) and act.n_xc_builds == int(fx["rks_n_veff"])
+    assert np.abs(np.asarray(d) - fx["rks_dm"]).max() < 1e-10 and np.abs(hz - fx["rks_huz"]).max() < 1e-10
+    assert np.abs(e - fx["rks_e"]).max() < 1e-10
+    assert abs(float(np.asarray(tr[-1]["energy"])) - float(fx["rks_energy"])) < 1e-7  # energy of the last cycle ~ converged
+    # closed shell: the restricted result is the spin-summed unrestricted one (to the two loops' stopping thresholds)
+    assert np.abs(np.asarray(d) - fx["ks_dm"].sum(axis=0)).max() < 1e-7
+
+
 def test_xc_derivatives_by_automatic_differentiation_match_finite_differences():
     """The Jet (forward-mode AD) derivatives of the B3LYP energy density against central differences, spin-polarised."""
     rng = np.random.default_rng(3)

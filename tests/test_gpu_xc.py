@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from nbed_b200 import B200UHF, B200UKS, LocalizedSystem, NbdError, huzinaga_scf, mu_embed
+from nbed_b200 import B200RKS, B200UHF, B200UKS, LocalizedSystem, NbdError, huzinaga_scf, mu_embed
 from oracle import gto_restatement as g
 from oracle import nbed_restatement as nr
 from oracle import pyscf_restatement as ps
@@ -99,6 +99,33 @@ def test_kohn_sham_huzinaga_loop_against_the_unmodified_reference(ctx, ksp):
     hf = B200UHF(ctx, p["s"], p["h"], (4, 4), max_cycle=40, conv_tol=1e-9)
     _, _, d_hf, _, _ = huzinaga_scf(hf, p["v_emb"], ls.dm_enviro, dm_conv_tol=1e-7)
     assert np.abs(np.asarray(d_hf) - np.asarray(d)).max() > 1e-4
+
+
+def test_restricted_kohn_sham_huzinaga_loop_against_the_unmodified_reference(ctx, ksp):
+    """The RKS object type (reference tests/test_scf.py:19-40): rank-2 inputs, `-1/2` Huzinaga factor, scalar
+    calculate_ks_energy = ecoul + exc + tr[D (h + Huz + V)], nr_rks as nr_uks of (D/2, D/2) on the device - against the
+    fixture of the unmodified reference loop over the stub RKS object and per cycle against the oracle."""
+    p = ksp
+    fx = np.load(os.path.join(GOLD, "reference_runs_ks.npz"))
+    ctx.load_cderi(p["cderi"])
+    act = B200RKS(ctx, p["s"], p["h"], (4, 4), xc="b3lyp", grids=(p["coords"], p["weights"]), basis=p["basis"],
+                  max_cycle=40, conv_tol=1e-9)
+    v, gam = p["v_emb"][0], 2.0 * p["dm_env"][0]
+    c, e, d, hz, conv, info = huzinaga_scf(act, v, gam, dm_conv_tol=1e-7, return_info=True)
+    assert conv == bool(fx["rks_conv"]) and np.asarray(d).shape == (7, 7)
+    assert np.abs(np.asarray(d) - fx["rks_dm"]).max() < 1e-8 and np.abs(hz - fx["rks_huz"]).max() < 1e-7
+    assert np.abs(e[:4] - fx["rks_e"][:4]).max() < 1e-8
+    ref = xcr.DFRKS(p["s"], p["h"], p["cderi"], (4, 4), p["ao"], p["weights"], "b3lyp", max_cycle=40, conv_tol=1e-9)
+    tr = []
+    nr.huzinaga_scf(ref, v, gam, dm_conv_tol=1e-7, trace=tr)
+    assert abs(info["cycles"] - len(tr)) <= 1
+    k = min(info["cycles"], len(tr))
+    assert np.abs(info["trace"][:k, 0] - np.array([float(np.asarray(t["energy"])) for t in tr[:k]])).max() < 1e-8
+    # the host-side protocol method the unmodified reference loop would call: get_veff with its tags
+    veff = act.get_veff(dm=np.asarray(d))
+    ref_veff = ref.get_veff(dm=np.asarray(d))
+    assert np.abs(np.asarray(veff) - np.asarray(ref_veff)).max() < 1e-9
+    assert abs(veff.ecoul - ref_veff.ecoul) < 1e-9 and abs(veff.exc - ref_veff.exc) < 1e-9
 
 
 def test_kohn_sham_mu_shift_path(ctx, ksp):
