@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import NBD_HUZINAGA, NBD_MU_SHIFT, NbdError, ScfResult, f64, pinned_empty, ptr
+from ._lib import NBD_HUZINAGA, NBD_MU_SHIFT, NbdError, ScfResult, f64, pinned_empty, ptr, result_empty
 
 TIMER_KEYS = (
     "jk_x", "jk_rho", "jk_j", "jk_k", "jk_total", "allreduce", "fock", "diis", "orth", "eigh", "density", "energy",
@@ -177,8 +177,8 @@ class B200Context:
         sg = None
         if signs is not None:
             sg = np.concatenate([f64(s).ravel() for s in signs]) if ncol.sum() else np.zeros(1)
-        vj = np.empty((nset, n, n)) if with_j else None
-        vk = np.empty((nset, n, n)) if with_k else None
+        vj = result_empty((nset, n, n)) if with_j else None
+        vk = result_empty((nset, n, n)) if with_k else None
         self._ck(self._lib.nbd_jk(self._h, nset, ptr(ncol), ptr(flat), ptr(sg), ptr(vj), ptr(vk)))
         return vj, vk
 
@@ -186,8 +186,8 @@ class B200Context:
         dm = f64(dm)
         shape = dm.shape
         dms = dm.reshape(-1, self.nao, self.nao)
-        vj = np.empty_like(dms) if with_j else None
-        vk = np.empty_like(dms) if with_k else None
+        vj = result_empty(dms.shape) if with_j else None
+        vk = result_empty(dms.shape) if with_k else None
         self._ck(self._lib.nbd_jk_dm(self._h, dms.shape[0], ptr(dms), ptr(vj), ptr(vk)))
         return (vj.reshape(shape) if with_j else None), (vk.reshape(shape) if with_k else None)
 
@@ -235,7 +235,7 @@ class B200Context:
     def huzinaga_scf(self, max_cycle, conv_tol, dm_conv_tol=1e-6, use_diis=True, dm0=None):
         n, ns = self.nao, self._nspin
         shape = (n, n) if ns == 1 else (2, n, n)
-        c, dm, huz = np.empty(shape), np.empty(shape), np.empty(shape)
+        c, dm, huz = result_empty(shape), result_empty(shape), result_empty(shape)
         e = np.empty(shape[:-1])
         trace = np.zeros((max_cycle, 3))
         res = ScfResult()
@@ -250,7 +250,7 @@ class B200Context:
     def mu_scf(self, max_cycle, conv_tol, e_nuc, dm0):
         n, ns = self.nao, self._nspin
         shape = (n, n) if ns == 1 else (2, n, n)
-        c, dm, vhf = np.empty(shape), np.empty(shape), np.empty(shape)
+        c, dm, vhf = result_empty(shape), result_empty(shape), result_empty(shape)
         e, occ = np.empty(shape[:-1]), np.empty(shape[:-1])
         trace = np.zeros((max_cycle + 1, 3))
         res = ScfResult()
@@ -276,7 +276,7 @@ class B200Context:
         ca = f64(ca)
         m = ca.shape[1]
         cbp = None if cb is None else f64(cb)
-        out = np.empty((4, m, m, m, m))
+        out = result_empty((4, m, m, m, m))
         self._ck(self._lib.nbd_ao2mo(self._h, m, ptr(ca), ptr(cbp), ptr(out)))
         return out
 
@@ -293,7 +293,7 @@ class B200Context:
         one, two = f64(one), f64(two)
         m = one.shape[-1]
         h1 = np.empty((2 * m, 2 * m))
-        h2 = np.empty((2 * m,) * 4)
+        h2 = result_empty((2 * m,) * 4)
         self._ck(self._lib.nbd_spinorb_from_spatial(self._h, m, ptr(one), ptr(two), float(eq_tol),
                                                     float(two_body_scale), ptr(h1), ptr(h2)))
         return h1, h2
@@ -306,7 +306,7 @@ class B200Context:
         nspin_h = 1 if hcore.ndim == 2 else 2
         cbp = None if cb is None else f64(cb)
         h1 = np.empty((2 * m, 2 * m))
-        h2 = np.empty((2 * m,) * 4)
+        h2 = result_empty((2 * m,) * 4)
         self._ck(self._lib.nbd_build_hamiltonian(self._h, m, nspin_h, ptr(hcore), ptr(ca), ptr(cbp), float(eq_tol),
                                                  float(two_body_scale), ptr(h1), ptr(h2)))
         return h1, h2

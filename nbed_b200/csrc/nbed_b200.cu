@@ -140,7 +140,10 @@ struct nbd_ctx {
   cudaStream_t stream2 = nullptr;
   cusolverDnHandle_t solver2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // [0,1] lane 0 (main stream), [2,3] lane 1 (copy stream)
+  cudaStream_t stream3 = nullptr;  // copy stream of the early result export (nbd_huzinaga_scf)
+  cudaEvent_t ev_export = nullptr;
+  PinnedBuf pinned2;
   int overlap = 1;
   int eig_threads = 1;  // second spin's full eigensolve issued from a helper thread on the side stream
   int dist_eig = 1;
@@ -151,6 +154,7 @@ struct nbd_ctx {
   int jpass_ctas_per_sm = 2;
   int x_cache = 1;        // reuse X = S^-1/2 across nbd_scf_setup calls with a bit-identical overlap matrix
   int x_valid_n = 0;      // nao the cached S / X belong to (0 = none)
+  int early_export = 1;   // nbd_huzinaga_scf copies D / Huz to the host on a copy stream while the final eigensolve runs
   int jpass_safe = 1;     // 0: pass 2 releases a ring stage before its loads are known to have returned (experiments)
   int syrk_mode = 1;      // 1: the K Gram runs as the stream-K symmetric rank-k kernel (syrk.cuh) when the shape allows
   int syrk_ctas = 0;      // CTAs of that kernel (0 = one per SM)
@@ -180,6 +184,7 @@ struct nbd_ctx {
   DBuf<int> d_seq, d_inv;
   DBuf<double> stage;  // packed-row staging for upload / download
   PinnedBuf pinned;
+  PinnedBuf rb;  // small read-backs of the SCF loop (subspace_host.cuh: d2h_small)
 
   // ---- J/K workspaces ----
   DBuf<double> d_orb, d_wt, d_X, d_rho, d_jpart, d_jk;  // d_jk = [J sets | K sets] contiguous (all-reduce buffer)
@@ -796,11 +801,15 @@ static void parallel_memcpy(char* dst, const char* src, size_t n) {
   memcpy(dst, src, std::min(n, part));
   for (int t = 1; t < T; ++t) f[t - 1].get();
 }
-static void staged_copy(nbd_ctx* c, char* host, char* dev, size_t bytes, bool to_host) {
-  char* st = (char*)c->pinned.ensure(2 * STAGE_CHUNK);
-  if (!c->ev_stage[0]) {
-    NBD_CUDA(cudaEventCreateWithFlags(&c->ev_stage[0], cudaEventDisableTiming));
-    NBD_CUDA(cudaEventCreateWithFlags(&c->ev_stage[1], cudaEventDisableTiming));
+// lane 0: the library's stream and staging buffers; lane 1: the copy stream (a second pair of staging buffers), used by
+// the early export of D / Huz that runs next to the final eigensolve.
+static void staged_copy(nbd_ctx* c, char* host, char* dev, size_t bytes, bool to_host, int lane = 0) {
+  char* st = (char*)(lane ? c->pinned2 : c->pinned).ensure(2 * STAGE_CHUNK);
+  cudaEvent_t* evs = c->ev_stage + 2 * lane;
+  cudaStream_t stream = lane ? c->stream3 : c->stream;
+  if (!evs[0]) {
+    NBD_CUDA(cudaEventCreateWithFlags(&evs[0], cudaEventDisableTiming));
+    NBD_CUDA(cudaEventCreateWithFlags(&evs[1], cudaEventDisableTiming));
   }
   const size_t nch = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
   if (to_host) {
@@ -809,9 +818,9 @@ static void staged_copy(nbd_ctx* c, char* host, char* dev, size_t bytes, bool to
       const int b = (int)(i & 1);
       const size_t off = i * STAGE_CHUNK, n = std::min(STAGE_CHUNK, bytes - off);
       if (fut[b].valid()) fut[b].get();  // staging buffer b is free again
-      NBD_CUDA(cudaMemcpyAsync(st + b * STAGE_CHUNK, dev + off, n, cudaMemcpyDeviceToHost, c->stream));
-      NBD_CUDA(cudaEventRecord(c->ev_stage[b], c->stream));
-      cudaEvent_t ev = c->ev_stage[b];
+      NBD_CUDA(cudaMemcpyAsync(st + b * STAGE_CHUNK, dev + off, n, cudaMemcpyDeviceToHost, stream));
+      NBD_CUDA(cudaEventRecord(evs[b], stream));
+      cudaEvent_t ev = evs[b];
       char* src = st + b * STAGE_CHUNK;
       char* dst = host + off;
       const int dev_id = c->device;
@@ -827,13 +836,13 @@ static void staged_copy(nbd_ctx* c, char* host, char* dev, size_t bytes, bool to
     for (size_t i = 0; i < nch; ++i) {
       const int b = (int)(i & 1);
       const size_t off = i * STAGE_CHUNK, n = std::min(STAGE_CHUNK, bytes - off);
-      if (i >= 2) NBD_CUDA(cudaEventSynchronize(c->ev_stage[b]));  // DMA out of staging buffer b has finished
+      if (i >= 2) NBD_CUDA(cudaEventSynchronize(evs[b]));  // DMA out of staging buffer b has finished
       parallel_memcpy(st + b * STAGE_CHUNK, host + off, n);
-      NBD_CUDA(cudaMemcpyAsync(dev + off, st + b * STAGE_CHUNK, n, cudaMemcpyHostToDevice, c->stream));
-      NBD_CUDA(cudaEventRecord(c->ev_stage[b], c->stream));
+      NBD_CUDA(cudaMemcpyAsync(dev + off, st + b * STAGE_CHUNK, n, cudaMemcpyHostToDevice, stream));
+      NBD_CUDA(cudaEventRecord(evs[b], stream));
     }
-    NBD_CUDA(cudaEventSynchronize(c->ev_stage[0]));
-    NBD_CUDA(cudaEventSynchronize(c->ev_stage[1]));
+    NBD_CUDA(cudaEventSynchronize(evs[0]));
+    NBD_CUDA(cudaEventSynchronize(evs[1]));
   }
 }
 static void h2d(nbd_ctx* c, double* dst, const double* src, size_t count) {
@@ -851,6 +860,17 @@ static void d2h(nbd_ctx* c, double* dst, const double* src, size_t count) {
     return;
   }
   NBD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+}
+// Device -> host copy on the copy stream (lane 1), blocking: for a helper thread that exports results which are already
+// final while the main thread keeps the library's stream busy.  The caller has made stream3 wait for the producers.
+static void d2h_lane1(nbd_ctx* c, double* dst, const double* src, size_t count) {
+  const size_t bytes = count * sizeof(double);
+  if (bytes >= (8u << 20) && host_is_pageable(dst)) {
+    staged_copy(c, (char*)dst, (char*)src, bytes, true, 1);
+    return;
+  }
+  NBD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream3));
+  NBD_CUDA(cudaStreamSynchronize(c->stream3));
 }
 
 extern "C" {
@@ -903,6 +923,8 @@ int nbd_destroy(nbd_ctx* c) {
   for (auto e : c->ev_stage)
     if (e) cudaEventDestroy(e);
   if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->stream3) cudaStreamDestroy(c->stream3);
+  if (c->ev_export) cudaEventDestroy(c->ev_export);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return NBD_OK;
@@ -931,6 +953,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "jpass_safe") c->jpass_safe = (int)value;
   else if (k == "copy_threads") g_copy_threads = (int)value;
   else if (k == "x_cache") { if (c->x_cache != (int)value) c->x_valid_n = 0; c->x_cache = (int)value; }
+  else if (k == "early_export") c->early_export = (int)value;
   else if (k == "jpass_sm_mod") c->jpass_sm_mod = (int)value;
   else if (k == "jpass_sm_keep") c->jpass_sm_keep = (int)value;
   else if (k == "jpass_ctas_per_sm") c->jpass_ctas_per_sm = (int)value;

@@ -128,7 +128,9 @@ static void scf_diagonalise_lowdin(nbd_ctx* c, bool allow_subspace = false, bool
     // computed by exactly one rank).  Replaces 4 n^3 replicated flop per spin by 4 n^3 / N + 8 n^2 bytes of NVLink.
     const int rpr = (n + c->world - 1) / c->world, r0 = std::min(n, c->rank * rpr), rows = std::min(n, r0 + rpr) - r0;
     const long pad = (long)c->world * rpr * n;
-    double* Fp = c->Fpad.ensure((size_t)c->nspin * pad);
+    // when the row blocks tile the matrix exactly the all-gather assembles F' in place, otherwise through a padded copy
+    const bool in_place = pad == nn;
+    double* Fp = in_place ? c->T2.p : c->Fpad.ensure((size_t)c->nspin * pad);
     {
       StageScope ts(c->timers, c->stream, "orth");
       if (rows > 0) {
@@ -143,7 +145,7 @@ static void scf_diagonalise_lowdin(nbd_ctx* c, bool allow_subspace = false, bool
         r = g_nccl.AllGather(Fp + s * pad + (long)c->rank * rpr * n, Fp + s * pad, (size_t)rpr * n, ncclDouble, c->comm, c->stream);
       if (r == ncclSuccess) r = g_nccl.GroupEnd();
       if (r != ncclSuccess) fail(NBD_ERR_CUDA, "ncclAllGather (F'): %s", g_nccl.GetErrorString(r));
-      for (int s = 0; s < c->nspin; ++s)
+      for (int s = 0; s < c->nspin && !in_place; ++s)
         NBD_CUDA(cudaMemcpyAsync(c->T2.p + s * nn, Fp + s * pad, sizeof(double) * nn, cudaMemcpyDeviceToDevice, c->stream));
     }
   } else {
@@ -212,8 +214,9 @@ static void scf_traces(nbd_ctx* c, const double* a, const double* b, const doubl
   LAUNCH_CHECK(c);
   scf_traces_final_kernel<<<1, 256, 0, c->stream>>>(part, REDUCE_BLOCKS, 4 * c->nspin, out);
   LAUNCH_CHECK(c);
-  d2h(c, out8, out, 4 * c->nspin);
+  const double* h = d2h_small(c, 3, out, 4 * c->nspin);
   NBD_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 4 * c->nspin; ++i) out8[i] = h[i];
 }
 
 // ---- DIIS (pyscf/lib/diis.py:DIIS.update; CDIIS pushes its own error vector) ------------------------
@@ -255,8 +258,7 @@ static void diis_update(nbd_ctx* c, DiisState& d, double* x, const double* errve
   LAUNCH_CHECK(c);
   multidot_final_kernel<<<1, 256, 0, c->stream>>>(part, REDUCE_BLOCKS, nd, out + 16);
   LAUNCH_CHECK(c);
-  double hrow[9];
-  d2h(c, hrow, out + 16, nd);
+  const double* hrow = d2h_small(c, 4, out + 16, nd);
   NBD_CUDA(cudaStreamSynchronize(c->stream));
   const int ldh = d.space + 1;
   for (int i = 0; i < nd; ++i) {
@@ -493,6 +495,7 @@ extern "C" int nbd_huzinaga_scf(nbd_ctx* c, int max_cycle, double conv_tol, doub
     const int eig_mode_in = c->eig_mode;
     double eprev[2] = {0.0, 0.0}, e[2] = {0.0, 0.0}, nd = 0.0;
     int conv = 0, cycles = 0;
+    bool exported = false;  // D / Huz of the accepted attempt already sit in the caller's buffers
     for (int attempt = 0; attempt < 2; ++attempt) {
     HuzLoop L;
     c->sub_valid = false;  // every SCF run starts from scratch (cold block / full diagonalisation / the caller's density)
@@ -527,8 +530,29 @@ extern "C" int nbd_huzinaga_scf(nbd_ctx* c, int max_cycle, double conv_tol, doub
     const bool tracked = !c->last_eig_full;
     double theta[2][32];
     memcpy(theta, c->sub_theta, sizeof theta);
+    // D and Huz are final here; only (C, eps) still need the full-spectrum solve.  Their copies to the caller's buffers
+    // (2 x 30 MB at n = 1376, through the staging pipeline when the destination is pageable) run from a helper thread on
+    // the copy stream while this thread drives the eigensolve.
+    std::future<void> early;
+    bool exported_early = false;
+    if (tracked && c->early_export && (dm || huz)) {
+      if (!c->stream3) NBD_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+      if (!c->ev_export) NBD_CUDA(cudaEventCreateWithFlags(&c->ev_export, cudaEventDisableTiming));
+      NBD_CUDA(cudaEventRecord(c->ev_export, c->stream));
+      NBD_CUDA(cudaStreamWaitEvent(c->stream3, c->ev_export, 0));
+      const int dev_id = c->device;
+      const size_t cnt = (size_t)c->nspin * nn;
+      const double *dD = c->D.p, *dH = c->Huz.p;
+      early = std::async(std::launch::async, [=] {
+        NBD_CUDA(cudaSetDevice(dev_id));
+        if (dm) d2h_lane1(c, dm, dD, cnt);
+        if (huz) d2h_lane1(c, huz, dH, cnt);
+      });
+      exported_early = true;
+    }
     scf_complete_spectrum(c);
     check_devinfo(c, c->nspin, "Fock eigendecomposition");
+    if (early.valid()) early.get();
     if (tracked) {
       double worst = 0.0;
       std::vector<double> w(32);
@@ -544,10 +568,11 @@ extern "C" int nbd_huzinaga_scf(nbd_ctx* c, int max_cycle, double conv_tol, doub
         continue;
       }
     }
+    exported = exported_early;
     break;
     }  // attempt
     c->eig_mode = eig_mode_in;
-    scf_export(c, mo_coeff, mo_energy, dm, huz, c->Huz.p);
+    scf_export(c, mo_coeff, mo_energy, exported ? nullptr : dm, exported ? nullptr : huz, c->Huz.p);
     if (result) {
       result->converged = conv;
       result->cycles = cycles;

@@ -426,21 +426,24 @@ __global__ void sub_scatter_block_kernel(const double* __restrict__ V, double* _
 }
 
 // ---- spectral bounds: a few Lanczos steps (Zhou & Li), then ||dF||_F updates while the block is tracked ---------
-// One Lanczos step per spin: w = A v - beta vprev, part[b][blk] = {sum_i w_i v_i, sum_i w_i^2} over the block's rows
-// (one warp per row, 8 rows per CTA; the host adds the blocks in order).
+// The recurrence scalars live on the device (coef[b][0..15] = alpha_j, coef[b][16..32] = beta_j, beta_0 = 0), so a whole
+// run is one stream of launches and ONE read-back (round 2: ten host round trips per run before).
+constexpr int SUB_LZ_COEF = 40;  // doubles per spin in the coefficient array
+// One Lanczos step per spin: w = A v - beta_j vprev, part[b][blk] = {sum_i w_i v_i, sum_i w_i^2} over the block's rows
+// (one warp per row, 8 rows per CTA; sub_lanczos_scalars_kernel adds the blocks in order).
 __global__ void __launch_bounds__(256) sub_lanczos_matvec_kernel(const double* __restrict__ Aall, const double* __restrict__ vall,
-                                                                 const double* __restrict__ vprevall, double beta0, double beta1,
-                                                                 double* __restrict__ wall, double* __restrict__ part, int n) {
+                                                                 const double* __restrict__ vprevall, const double* __restrict__ coef,
+                                                                 int j, double* __restrict__ wall, double* __restrict__ part, int n) {
   __shared__ double red[8][2];
   const int b = blockIdx.y;
   const double* A = Aall + (long)b * n * n;
   const double* v = vall + (long)b * n;
-  const double beta = b == 0 ? beta0 : beta1;
+  const double beta = __ldcg(coef + b * SUB_LZ_COEF + 16 + j);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + warp;
   double s = 0.0;
   if (i < n)
-    for (int j = lane; j < n; j += 32) s = fma(A[(long)i * n + j], __ldcg(v + j), s);
+    for (int jj = lane; jj < n; jj += 32) s = fma(A[(long)i * n + jj], __ldcg(v + jj), s);
   s = warp_sum(s);
   if (lane == 0) {
     double wv = 0.0, ww = 0.0;
@@ -461,16 +464,35 @@ __global__ void __launch_bounds__(256) sub_lanczos_matvec_kernel(const double* _
     part[((long)b * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = t;
   }
 }
-// vnext = (w - alpha v) / beta_next   (per spin scalars)
+// alpha_j = sum_blk part[.][0], beta_{j+1} = sqrt(max(0, sum_blk part[.][1] - alpha_j^2)); one CTA of 32 threads per spin,
+// blocks added in index order (the order the host used to add them in)
+__global__ void sub_lanczos_scalars_kernel(const double* __restrict__ part, int nblk, int j, double* __restrict__ coef) {
+  __shared__ double acc[2];
+  const int b = blockIdx.x;
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int k = 0; k < nblk; ++k) t += __ldcg(part + ((long)b * nblk + k) * 2 + threadIdx.x);
+    acc[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double a = acc[0];
+    coef[b * SUB_LZ_COEF + j] = a;
+    coef[b * SUB_LZ_COEF + 16 + j + 1] = sqrt(fmax(0.0, acc[1] - a * a));
+  }
+}
+// vnext = (w - alpha_j v) / beta_{j+1}   (a vanishing beta gives non-finite vectors; the host cuts the run there)
 __global__ void sub_lanczos_update_kernel(const double* __restrict__ w, const double* __restrict__ v, double* __restrict__ vnext,
-                                          double alpha0, double alpha1, double ib0, double ib1, int n) {
+                                          const double* __restrict__ coef, int j, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (i >= n) return;
   const long o = (long)b * n + i;
-  vnext[o] = (__ldcg(w + o) - (b == 0 ? alpha0 : alpha1) * __ldcg(v + o)) * (b == 0 ? ib0 : ib1);
+  const double alpha = __ldcg(coef + b * SUB_LZ_COEF + j), beta = __ldcg(coef + b * SUB_LZ_COEF + 16 + j + 1);
+  vnext[o] = (__ldcg(w + o) - alpha * __ldcg(v + o)) * (1.0 / beta);
 }
 // part[b][blk] = sum over the block's slice of (A - B)^2   (gridDim.x slices per matrix, fixed order)
-__global__ void __launch_bounds__(256) sub_diffnorm_kernel(const double* __restrict__ A, const double* __restrict__ B, long count,
+// and B <- A (the matrix the next cycle compares with) in the same pass
+__global__ void __launch_bounds__(256) sub_diffnorm_kernel(const double* __restrict__ A, double* __restrict__ B, long count,
                                                            double* __restrict__ part) {
   __shared__ double red[32];
   const int b = blockIdx.y;
@@ -478,7 +500,9 @@ __global__ void __launch_bounds__(256) sub_diffnorm_kernel(const double* __restr
   const long e0 = per * blockIdx.x, e1 = e0 + per < count ? e0 + per : count;
   double s = 0.0;
   for (long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-    const double d = __ldcg(A + (long)b * count + e) - __ldcg(B + (long)b * count + e);
+    const double av = __ldcg(A + (long)b * count + e);
+    const double d = av - __ldcg(B + (long)b * count + e);
+    B[(long)b * count + e] = av;
     s = fma(d, d, s);
   }
   s = block_sum(s, red);

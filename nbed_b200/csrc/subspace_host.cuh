@@ -6,6 +6,8 @@ static int sub_block_size(const nbd_ctx* c) {
   int omax = 0;
   for (int s = 0; s < c->nspin; ++s) omax = std::max(omax, c->nspin == 2 ? c->nelec[s] : (c->nelec[0] + c->nelec[1]) / 2);
   if (c->eig_mode != 1 || c->projector != NBD_HUZINAGA || c->nao < c->sub_min_nao || omax < 1) return 0;
+  // (a 32-vector block for <= 10 occupied orbitals was measured in round 2: 3 % fewer block products at C4, each twice
+  // as expensive - profiles/r02x_block32.md)
   if (omax <= 10) return 16;
   if (omax <= 24) return 32;
   return 0;
@@ -45,14 +47,27 @@ static void sub_init_from_full(nbd_ctx* c, const double* eigrows, const double* 
   c->sub_valid = true;
 }
 
+// Small device -> host read-backs go through a pinned scratch area: a pageable destination makes the driver stage the
+// copy, which costs several microseconds more per round trip - and the SCF loop makes ~10 of them per cycle.
+// `slot` separates read-backs that are in flight at the same time (slots of 4096 doubles).
+static double* rb_slot(nbd_ctx* c, int slot) { return (double*)c->rb.ensure((size_t)8 * 4096 * sizeof(double)) + (size_t)slot * 4096; }
+static double* d2h_small(nbd_ctx* c, int slot, const double* src, size_t count) {
+  NBD_REQUIRE(count <= 4096, NBD_ERR_STATE, "read-back of %zu doubles does not fit a slot", count);
+  double* h = rb_slot(c, slot);
+  NBD_CUDA(cudaMemcpyAsync(h, src, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return h;
+}
+
 // k-step Lanczos per spin (batched): up = theta_max + beta_k (+ 2 % of the Ritz spread), low = theta_min - beta_k.
 // Spins [s0, s0 + ns) of the problem; Fp, up, low are indexed by the LOCAL spin 0 .. ns-1 (the caller offsets them).
+// The recurrence scalars stay on the device; the host reads all of them back once and cuts the run at a breakdown.
 static void sub_lanczos_bounds(nbd_ctx* c, const double* Fp, double* up, double* low, int s0, int ns) {
   const int n = c->nao;
   const int steps = std::min(10, n);
   const int nblk = (n + 7) / 8;
-  double* buf = c->sLz.ensure((size_t)3 * ns * n + (size_t)2 * ns * nblk);
-  double *v = buf, *vprev = buf + (size_t)ns * n, *w = buf + (size_t)2 * ns * n, *part = buf + (size_t)3 * ns * n;
+  double* buf = c->sLz.ensure((size_t)3 * ns * n + (size_t)2 * ns * nblk + (size_t)2 * SUB_LZ_COEF);
+  double *v = buf, *vprev = buf + (size_t)ns * n, *w = buf + (size_t)2 * ns * n, *part = buf + (size_t)3 * ns * n,
+         *coef = part + (size_t)2 * ns * nblk;
   // deterministic start vector (same hash as the start block), normalised on the host
   std::vector<double> v0((size_t)ns * n);
   for (int s = 0; s < ns; ++s) {
@@ -71,31 +86,30 @@ static void sub_lanczos_bounds(nbd_ctx* c, const double* Fp, double* up, double*
   }
   h2d(c, v, v0.data(), v0.size());
   NBD_CUDA(cudaMemsetAsync(vprev, 0, sizeof(double) * ns * n, c->stream));
-  double alpha[2][16] = {}, beta[2][17] = {};
-  std::vector<double> hp((size_t)2 * ns * nblk);
-  int k = 0;
+  NBD_CUDA(cudaMemsetAsync(coef, 0, sizeof(double) * 2 * SUB_LZ_COEF, c->stream));
   for (int j = 0; j < steps; ++j) {
-    sub_lanczos_matvec_kernel<<<dim3(nblk, ns), 256, 0, c->stream>>>(Fp, v, vprev, beta[0][j], beta[1][j], w, part, n);
+    sub_lanczos_matvec_kernel<<<dim3(nblk, ns), 256, 0, c->stream>>>(Fp, v, vprev, coef, j, w, part, n);
     LAUNCH_CHECK(c);
-    d2h(c, hp.data(), part, hp.size());
-    NBD_CUDA(cudaStreamSynchronize(c->stream));
-    bool breakdown = false;
-    for (int s = 0; s < ns; ++s) {
-      double a = 0.0, ww = 0.0;
-      for (int b = 0; b < nblk; ++b) {
-        a += hp[((size_t)s * nblk + b) * 2];
-        ww += hp[((size_t)s * nblk + b) * 2 + 1];
-      }
-      alpha[s][j] = a;
-      beta[s][j + 1] = std::sqrt(std::max(0.0, ww - a * a));
-      if (!(beta[s][j + 1] > 1e-10 * (std::fabs(a) + 1e-300))) breakdown = true;
-    }
-    k = j + 1;
-    if (breakdown || k == steps) break;
-    sub_lanczos_update_kernel<<<dim3((n + 255) / 256, ns), 256, 0, c->stream>>>(w, v, vprev, alpha[0][j], alpha[1][j], 1.0 / beta[0][j + 1],
-                                                                                 1.0 / beta[1][j + 1], n);
+    sub_lanczos_scalars_kernel<<<ns, 32, 0, c->stream>>>(part, nblk, j, coef);
+    LAUNCH_CHECK(c);
+    if (j + 1 == steps) break;
+    sub_lanczos_update_kernel<<<dim3((n + 255) / 256, ns), 256, 0, c->stream>>>(w, v, vprev, coef, j, n);
     LAUNCH_CHECK(c);
     std::swap(v, vprev);
+  }
+  const double* hc = d2h_small(c, 2, coef, (size_t)2 * SUB_LZ_COEF);
+  NBD_CUDA(cudaStreamSynchronize(c->stream));
+  double alpha[2][16] = {}, beta[2][17] = {};
+  int k = 0;
+  for (int j = 0; j < steps; ++j) {
+    bool breakdown = false;
+    for (int s = 0; s < ns; ++s) {
+      alpha[s][j] = hc[s * SUB_LZ_COEF + j];
+      beta[s][j + 1] = hc[s * SUB_LZ_COEF + 16 + j + 1];
+      if (!(beta[s][j + 1] > 1e-10 * (std::fabs(alpha[s][j]) + 1e-300))) breakdown = true;
+    }
+    k = j + 1;
+    if (breakdown) break;
   }
   for (int s = 0; s < ns; ++s) {
     double lo, hi;
@@ -110,34 +124,43 @@ static void sub_lanczos_bounds(nbd_ctx* c, const double* Fp, double* up, double*
 // Interval [low, up] containing the spectrum of Fp (per spin) for the Chebyshev filter.  Mode 1: the bounds of the
 // last matrix widened by the Frobenius norm of the change (rigorous: |lambda(A + E) - lambda(A)| <= ||E||_2 <= ||E||_F),
 // refreshed by a new Lanczos run whenever they have drifted by a quarter of the width.  Mode 0: row-sum bound.
-static void sub_spectral_bounds(nbd_ctx* c, const double* Fp, double* up, double* low, int s0, int ns) {
+// Two halves, so that the read-back of ||dF'||_F rides on the first Rayleigh-Ritz step's host round trip:
+// sub_bounds_begin launches the norm (and the copy of F' the next cycle compares with) and returns the host address the
+// partial sums will arrive at; sub_bounds_finish - after a stream synchronisation - turns them into bounds.
+static const double* sub_bounds_begin(nbd_ctx* c, const double* Fp, int s0, int ns) {
+  const long nn = (long)c->nao * c->nao;
+  if (c->sub_bound_mode == 0) return nullptr;
+  constexpr int NBLK = 64;
+  double* prev = c->sFprev.ensure((size_t)c->nspin * nn) + (long)s0 * nn;
+  if (!c->sub_bounds_valid) {
+    NBD_CUDA(cudaMemcpyAsync(prev, Fp, sizeof(double) * ns * nn, cudaMemcpyDeviceToDevice, c->stream));
+    return nullptr;
+  }
+  double* bp = c->sBound.ensure((size_t)2 * NBLK);
+  sub_diffnorm_kernel<<<dim3(NBLK, ns), 256, 0, c->stream>>>(Fp, prev, nn, bp);
+  LAUNCH_CHECK(c);
+  return d2h_small(c, 1, bp, (size_t)ns * NBLK);
+}
+static void sub_bounds_finish(nbd_ctx* c, const double* Fp, const double* hb, double* up, double* low, int s0, int ns) {
   const int n = c->nao;
-  const long nn = (long)n * n;
   if (c->sub_bound_mode == 0) {
     const int nblk = (n + 7) / 8;
     double* bp = c->sBound.ensure((size_t)2 * nblk);
     sub_gershgorin_kernel<<<dim3(nblk, ns), 256, 0, c->stream>>>(Fp, n, bp);
     LAUNCH_CHECK(c);
-    std::vector<double> hb((size_t)ns * nblk);
-    d2h(c, hb.data(), bp, hb.size());
+    std::vector<double> g((size_t)ns * nblk);
+    d2h(c, g.data(), bp, g.size());
     NBD_CUDA(cudaStreamSynchronize(c->stream));
     for (int s = 0; s < ns; ++s) {
       up[s] = 0.0;
-      for (int k = 0; k < nblk; ++k) up[s] = std::max(up[s], hb[(size_t)s * nblk + k]);
+      for (int k = 0; k < nblk; ++k) up[s] = std::max(up[s], g[(size_t)s * nblk + k]);
       low[s] = -up[s];
     }
     return;
   }
   constexpr int NBLK = 64;
-  double* prev = c->sFprev.ensure((size_t)c->nspin * nn) + (long)s0 * nn;
-  bool refresh = !c->sub_bounds_valid;
+  bool refresh = !c->sub_bounds_valid || !hb;
   if (!refresh) {
-    double* bp = c->sBound.ensure((size_t)2 * NBLK);
-    sub_diffnorm_kernel<<<dim3(NBLK, ns), 256, 0, c->stream>>>(Fp, prev, nn, bp);
-    LAUNCH_CHECK(c);
-    std::vector<double> hb((size_t)ns * NBLK);
-    d2h(c, hb.data(), bp, hb.size());
-    NBD_CUDA(cudaStreamSynchronize(c->stream));
     for (int s = 0; s < ns; ++s) {
       double d2 = 0.0;
       for (int k = 0; k < NBLK; ++k) d2 += hb[(size_t)s * NBLK + k];
@@ -158,7 +181,6 @@ static void sub_spectral_bounds(nbd_ctx* c, const double* Fp, double* up, double
     c->sub_up[s0 + s] = up[s];
     c->sub_low[s0 + s] = low[s];
   }
-  NBD_CUDA(cudaMemcpyAsync(prev, Fp, sizeof(double) * ns * nn, cudaMemcpyDeviceToDevice, c->stream));
   c->sub_bounds_valid = true;
 }
 
@@ -223,6 +245,8 @@ static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double
 
 // Tracks the KB lowest eigenvectors of spins [s0, s0 + ns) of Fp ([nspin][n][n], Lowdin basis) starting from c->sV.
 // On success c->sV holds the Ritz vectors, c->sub_theta the Ritz values; returns false when it did not converge.
+// Host round trips per Rayleigh-Ritz step: two (Gram matrices out / rotation in, residuals out), both through the pinned
+// read-back area; the norm ||F'_k - F'_{k-1}||_F that widens the filter interval arrives with the first of them.
 template <int KB>
 static bool sub_solve_t(nbd_ctx* c, const double* Fp_all, int s0, int ns) {
   const int n = c->nao;
@@ -232,20 +256,21 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp_all, int s0, int ns) {
   c->sub_is_cold = false;
   const int max_degree = 24, max_outer = cold ? 24 : 14;
   const double tol = 1e-10;
-  // device views of the spins handled here
+  // device views of the spins handled here (sV / sY are re-read from the context: the rotation swaps them)
   const double* Fp = Fp_all + (long)s0 * nn;
-  double *sV = c->sV.p + s0 * blk, *sY = c->sY.p + s0 * blk, *sZ = c->sZ.p + s0 * blk, *sW = c->sW.p + s0 * blk,
-         *sAV = c->sAV.p + s0 * blk;
+  double *sZ = c->sZ.p + s0 * blk, *sW = c->sW.p + s0 * blk, *sAV = c->sAV.p + s0 * blk;
   double *sG = c->sG.p + (long)s0 * 2 * KB * KB, *sGpart = c->sGpart.p + (long)s0 * NBLK * 2 * KB * KB,
          *sM = c->sM.p + (long)s0 * KB * KB, *sTheta = c->sTheta.p + (long)s0 * KB, *sRpart = c->sRpart.p + (long)s0 * NBLK * KB;
   unsigned int* ticket = c->sTicket.p + 2048 + s0;
   double bound[2] = {0, 0}, lowb[2] = {0, 0}, bu_used[2] = {0, 0};
-  sub_spectral_bounds(c, Fp, bound, lowb, s0, ns);
+  const double* hb = sub_bounds_begin(c, Fp, s0, ns);
   const double one[2] = {1.0, 1.0}, zero[2] = {0.0, 0.0};
-  double* cur = sV;  // block to Rayleigh-Ritz next
+  double* cur = c->sV.p + s0 * blk;  // block to Rayleigh-Ritz next
   double worst_prev = -1.0;
   int deg_prev = 0;
+  std::vector<double> M((size_t)ns * KB * KB), th((size_t)ns * KB);
   for (int outer = 0; outer < max_outer; ++outer) {
+    double *sV = c->sV.p + s0 * blk, *sY = c->sY.p + s0 * blk;
     if (outer > 0) {
       // scaled Chebyshev filter of degree `degree` damping [a, bound] (Zhou & Saad), per spin
       double e[2], cc[2] = {0, 0}, sig[2], sig1[2], al[2];
@@ -291,11 +316,11 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp_all, int s0, int ns) {
     sub_apply<KB>(c, Fp, cur, nullptr, sW, one, zero, zero, ns);
     sub_gram_kernel<KB><<<dim3(NBLK, ns), 256, 0, c->stream>>>(cur, sW, sGpart, sG, ticket, n);
     LAUNCH_CHECK(c);
-    std::vector<double> G((size_t)ns * 2 * KB * KB), M((size_t)ns * KB * KB), th((size_t)ns * KB);
-    d2h(c, G.data(), sG, G.size());
+    const double* G = d2h_small(c, 0, sG, (size_t)ns * 2 * KB * KB);
     NBD_CUDA(cudaStreamSynchronize(c->stream));
+    if (outer == 0) sub_bounds_finish(c, Fp, hb, bound, lowb, s0, ns);  // G was copied before any Lanczos run reuses slot 2
     for (int s = 0; s < ns; ++s)
-      if (!sub_rayleigh_ritz(KB, G.data() + (size_t)s * 2 * KB * KB, G.data() + (size_t)s * 2 * KB * KB + KB * KB,
+      if (!sub_rayleigh_ritz(KB, G + (size_t)s * 2 * KB * KB, G + (size_t)s * 2 * KB * KB + KB * KB,
                              M.data() + (size_t)s * KB * KB, th.data() + (size_t)s * KB))
         return false;
     // a Ritz value above the assumed upper end of the spectrum: the filter interval was wrong, let the library decide
@@ -306,13 +331,15 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp_all, int s0, int ns) {
       }
     h2d(c, sM, M.data(), M.size());
     h2d(c, sTheta, th.data(), th.size());
-    // rotate into a buffer that is not `cur` (cur may alias sV / sY / sZ): use sAV for A V and the free one for V
+    // rotate into a buffer that is not `cur` (cur may alias sV / sY / sZ); if that buffer is sY, sV and sY trade places
     double* vout = (cur == sV) ? sY : sV;
     sub_rotate_kernel<KB><<<dim3(NBLK, ns), 256, 0, c->stream>>>(cur, sW, sM, sTheta, vout, sAV, sRpart, n);
     LAUNCH_CHECK(c);
-    if (vout != sV) NBD_CUDA(cudaMemcpyAsync(sV, vout, sizeof(double) * blk * ns, cudaMemcpyDeviceToDevice, c->stream));
-    std::vector<double> rp((size_t)ns * NBLK * KB);
-    d2h(c, rp.data(), sRpart, rp.size());
+    if (vout != sV) {
+      std::swap(c->sV.p, c->sY.p);
+      std::swap(c->sV.cap, c->sY.cap);
+    }
+    const double* rp = d2h_small(c, 0, sRpart, (size_t)ns * NBLK * KB);
     NBD_CUDA(cudaStreamSynchronize(c->stream));
     double worst = 0.0;
     for (int s = 0; s < ns; ++s) {
@@ -325,6 +352,7 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp_all, int s0, int ns) {
       }
     }
     ++c->sub_outer;
+    cur = c->sV.p + s0 * blk;
     if (worst < tol) return true;
     if (!cold && outer > 0 && deg_prev > 0 && worst_prev > 0.0 && worst < worst_prev)
       c->sub_rate = std::max(c->sub_rate, std::pow(worst / worst_prev, 1.0 / deg_prev));
