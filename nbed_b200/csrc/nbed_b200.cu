@@ -217,7 +217,8 @@ struct nbd_ctx {
   int sub_bound_mode = 1;
   int sub_adaptive = 1;   // filter degree of a tracked block from the observed residual reduction per degree
   double sub_rate = 0.0;  // slowest residual reduction per filter degree seen in the current SCF (0 = none yet)
-  int sub_apply_variant = 0;  // 0: cluster split-K block product (4-CTA clusters, DSMEM reduction); 1: one CTA per 16 rows
+  int sub_apply_variant = 0;  // 0: automatic (single-shot 8-CTA-cluster kernel when its grid is resident at once, else the 4-CTA-cluster ring kernel); 1: one CTA per 16 rows; 2: single-shot kernel; 3: ring kernel
+  int sub_pdl = 1;  // consecutive block products overlap through programmatic dependent launch
   int sub_cold = 1;  // 1: the initial guess starts the block from pseudo-random vectors (no library eigensolve)
   bool sub_bounds_valid = false, sub_is_cold = false;
   double sub_up[2] = {0, 0}, sub_low[2] = {0, 0}, sub_up_ref[2] = {0, 0}, sub_low_ref[2] = {0, 0};
@@ -962,6 +963,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "sub_bound") { c->sub_bound_mode = (int)value; c->sub_bounds_valid = false; }
   else if (k == "sub_cold") c->sub_cold = (int)value;
   else if (k == "sub_apply_variant") c->sub_apply_variant = (int)value;
+  else if (k == "sub_pdl") c->sub_pdl = (int)value;
   else if (k == "sub_adaptive") c->sub_adaptive = (int)value;
   else if (k == "dist_sub") c->dist_sub = (int)value;
   else if (k == "sub_min_nao") { c->sub_min_nao = (int)value; c->sub_valid = false; }

@@ -164,7 +164,9 @@ constexpr int sub_apply2_smem_bytes() {
   return (ring > red ? ring : red) + SUB2_ROWS * KB * 8;
 }
 
-template <int KB>
+// PDL = 1 (programmatic stream serialisation, see sub_apply3_kernel): the F' parts of the first ring stages are requested
+// before griddepcontrol.wait, everything that touches Y / Z / out behind it.
+template <int KB, int PDL = 0>
 __global__ void __launch_bounds__(128) sub_apply2_kernel(SubApplyArgs a) {
   constexpr int A_LD = SUB2_JCHUNK + 4, Y_LD = KB + 4, NI = KB / 8, MI = SUB2_ROWS / 8;
   constexpr int A_ST = SUB2_ROWS * A_LD, Y_ST = SUB2_JCHUNK * Y_LD;
@@ -187,10 +189,9 @@ __global__ void __launch_bounds__(128) sub_apply2_kernel(SubApplyArgs a) {
   for (int i = 0; i < MI; ++i)
 #pragma unroll
     for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  auto load = [&](int ch, int buf) {
+  auto load_a = [&](int ch, int buf) {
     const int j0 = ch * SUB2_JCHUNK;
     double* as = As + buf * A_ST;
-    double* ys = Ys + buf * Y_ST;
     if (vec) {
 #pragma unroll
       for (int q = 0; q < SUB2_ROWS * SUB2_JCHUNK / 2 / 128; ++q) {
@@ -210,6 +211,10 @@ __global__ void __launch_bounds__(128) sub_apply2_kernel(SubApplyArgs a) {
         cp_async8(as + r * A_LD + j, ok ? A + (long)gi * n + gj : A, ok);
       }
     }
+  };
+  auto load_y = [&](int ch, int buf) {
+    const int j0 = ch * SUB2_JCHUNK;
+    double* ys = Ys + buf * Y_ST;
 #pragma unroll
     for (int q = 0; q < SUB2_JCHUNK * KB / 2 / 128; ++q) {
       const int e = tid + 128 * q;
@@ -218,9 +223,19 @@ __global__ void __launch_bounds__(128) sub_apply2_kernel(SubApplyArgs a) {
       cp_async16(ys + j * Y_LD + c2, ok ? Y + (long)(j0 + j) * KB + c2 : Y, ok);
     }
   };
+  if (PDL) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < SUB2_STAGES - 1; ++s)
+      if (ch0 + s < ch1) load_a(ch0 + s, s);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
 #pragma unroll
   for (int s = 0; s < SUB2_STAGES - 1; ++s) {
-    if (ch0 + s < ch1) load(ch0 + s, s);
+    if (ch0 + s < ch1) {
+      if (!PDL) load_a(ch0 + s, s);
+      load_y(ch0 + s, s);
+    }
     cp_async_commit();
   }
   for (int ch = ch0; ch < ch1; ++ch) {
@@ -228,7 +243,10 @@ __global__ void __launch_bounds__(128) sub_apply2_kernel(SubApplyArgs a) {
     __syncthreads();
     {
       const int nx = ch + SUB2_STAGES - 1;
-      if (nx < ch1) load(nx, (nx - ch0) % SUB2_STAGES);
+      if (nx < ch1) {
+        load_a(nx, (nx - ch0) % SUB2_STAGES);
+        load_y(nx, (nx - ch0) % SUB2_STAGES);
+      }
       cp_async_commit();
     }
     const int buf = (ch - ch0) % SUB2_STAGES;
@@ -282,6 +300,143 @@ __global__ void __launch_bounds__(128) sub_apply2_kernel(SubApplyArgs a) {
     }
   }
   cluster_sync_all();  // the peers' shared memory stays alive until rank 0 has read it
+}
+
+// ---- single-shot bulk-copy variant (round 2, variant 2) --------------------------------------------------------
+// The ring of the kernel above walks 11 chunk steps per CTA, each a cp.async wait + CTA barrier: ~12 us per block
+// product although the bytes are worth 3-6 us of L2 bandwidth.  Here the contraction index is split over the EIGHT CTAs of
+// a cluster, so that a CTA's whole operand slab - 32 rows x n/8 columns of F' and n/8 rows of Y, 74 KB at n = 1376 - fits
+// in shared memory at once: one warp issues all bulk copies (TMA 1-D, one per matrix row / block row) in two halves on
+// two mbarriers, every warp owns 8 output rows over the whole slab (no reduction inside the CTA) and starts on the first
+// half while the second is still in flight.  The eight partial 32 x KB tiles are summed over DSMEM in rank order
+// (deterministic), each CTA finishing 4 rows, with the epilogue's Y / Z operands prefetched at kernel entry.
+// Three CTAs per SM: one spin's product (344 CTAs at n = 1376) is a single wave.  Needs even n (16-byte row starts).
+constexpr int SUB3_ROWS = 32;
+constexpr int SUB3_KS = 8;
+__host__ __device__ constexpr int sub_apply3_klen(int n) { return ((n + SUB3_KS - 1) / SUB3_KS + 15) / 16 * 16; }
+template <int KB>
+__host__ __device__ constexpr int sub_apply3_smem_bytes(int n) {
+  // [64 B barriers][A slab 32 x (KL + 4)][Y slab KL x (KB + 4)]; the CTA's partial tile reuses the A slab
+  return 64 + (SUB3_ROWS * (sub_apply3_klen(n) + 4) + sub_apply3_klen(n) * (KB + 4)) * 8;
+}
+
+// PDL = 1: launched with programmatic stream serialisation.  The CTA lets the next product of the chain start at once
+// (its barrier set-up and F' copies do not depend on this one) and itself touches Y / Z / out - the buffers the
+// previous product reads or writes - only behind griddepcontrol.wait, i.e. after that grid has completed.
+template <int KB, int PDL>
+__global__ void __launch_bounds__(128) sub_apply3_kernel(SubApplyArgs a) {
+  constexpr int NI = KB / 8, Y_LD = KB + 4;
+  extern __shared__ __align__(128) unsigned char s3[];
+  const int n = a.n, KL = sub_apply3_klen(n), P = KL + 4;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s3);
+  double* As = reinterpret_cast<double*>(s3 + 64);
+  double* Ys = As + SUB3_ROWS * P;
+  double* tile = As;  // [32][KB] after the product
+  const int ks = (int)cluster_ctarank();
+  const int rb = blockIdx.x, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const double* A = a.A + (long)b * n * n;
+  const double* Y = a.Y + (long)b * n * KB;
+  const int k0 = ks * KL;
+  const int len = max(0, min(n, k0 + KL) - k0);  // contraction indices of this CTA (even, as n and KL are)
+  const int half0 = min(len, KL / 2), half1 = len - half0;
+  const int rows_valid = min(SUB3_ROWS, n - rb * SUB3_ROWS);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&bar[0], (uint32_t)((rows_valid * half0 + half0 * KB) * 8));
+      mbar_expect_tx(&bar[1], (uint32_t)((rows_valid * half1 + half1 * KB) * 8));
+    }
+    __syncwarp();
+    if (lane < rows_valid) {
+      const double* src = A + (long)(rb * SUB3_ROWS + lane) * n + k0;
+      if (half0 > 0) bulk_g2s(As + lane * P, src, (uint32_t)(half0 * 8), &bar[0]);
+      if (half1 > 0) bulk_g2s(As + lane * P + half0, src + half0, (uint32_t)(half1 * 8), &bar[1]);
+    }
+  }
+  if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+  // epilogue operands of the 4 rows this CTA finishes (thread e < 4 KB): in flight while the slab arrives
+  const int erow = rb * SUB3_ROWS + 4 * ks + tid / KB;
+  const bool emine = tid < 4 * KB && erow < n;
+  double ey = 0.0, ez = 0.0;
+  if (emine) {
+    ey = __ldcg(Y + (long)erow * KB + tid % KB);
+    if (a.Z) ez = __ldcg(a.Z + (long)b * n * KB + (long)erow * KB + tid % KB);
+  }
+  if (warp != 0) {
+    // rows of the Y slab, padded pitch (conflict-free B fragments): warps 1-3 issue the 128-byte row copies
+    for (int j = tid - 32; j < len; j += 96)
+      bulk_g2s(Ys + j * Y_LD, Y + (long)(k0 + j) * KB, (uint32_t)(KB * 8), &bar[j < half0 ? 0 : 1]);
+  }
+  // contraction tail: zero up to the next multiple of 4 (disjoint from the bytes the copies write)
+  const int len4 = (len + 3) & ~3;
+  for (int e = tid; e < (len4 - len) * SUB3_ROWS; e += 128) As[(e % SUB3_ROWS) * P + len + e / SUB3_ROWS] = 0.0;
+  for (int e = tid; e < (len4 - len) * KB; e += 128) Ys[(len + e / KB) * Y_LD + e % KB] = 0.0;
+  __syncthreads();
+  // warp w: output rows [8 w, 8 w + 8) over the whole slab; two independent accumulator sets (alternate k4 steps)
+  double acc[2][NI][2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) acc[h][j][0] = acc[h][j][1] = 0.0;
+  const double* as = As + (8 * warp + gq) * P + tq;
+  const double* ys = Ys + tq * Y_LD + gq;
+  auto run = [&](int kb, int ke) {  // k4 steps [kb, ke), kb even count from a multiple of 8
+    int k = kb;
+    for (; k + 8 <= ke; k += 8) {
+      const double a0 = as[k], a1 = as[k + 4];
+      double b0[NI], b1[NI];
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        b0[j] = ys[k * Y_LD + 8 * j];
+        b1[j] = ys[(k + 4) * Y_LD + 8 * j];
+      }
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        dmma(acc[0][j], a0, b0[j]);
+        dmma(acc[1][j], a1, b1[j]);
+      }
+    }
+    for (; k < ke; k += 4) {
+      const double a0 = as[k];
+#pragma unroll
+      for (int j = 0; j < NI; ++j) dmma(acc[0][j], a0, ys[k * Y_LD + 8 * j]);
+    }
+  };
+  // the first half is KL / 2 long (a multiple of 8) whenever a second half exists
+  mbar_wait(&bar[0], 0);
+  run(0, half1 > 0 ? half0 : len4);
+  if (half1 > 0) {
+    mbar_wait(&bar[1], 0);
+    run(half0, len4);
+  }
+  __syncthreads();  // every warp is done with the A slab: it now holds this CTA's partial tile
+#pragma unroll
+  for (int j = 0; j < NI; ++j) {
+    double* t = tile + (8 * warp + gq) * KB + 8 * j + 2 * tq;
+    t[0] = acc[0][j][0] + acc[1][j][0];
+    t[1] = acc[0][j][1] + acc[1][j][1];
+  }
+  cluster_sync_all();  // all eight partial tiles are in place (release / acquire at cluster scope)
+  if (emine) {
+    const uint32_t t0 = smem_u32(tile + (4 * ks) * KB + tid);
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < SUB3_KS; ++q) s += dsmem_ld(dsmem_addr(t0, (uint32_t)q));
+    const double alpha = b == 0 ? a.alpha[0] : a.alpha[1], shift = b == 0 ? a.shift[0] : a.shift[1],
+                 beta = b == 0 ? a.beta[0] : a.beta[1];
+    double v = alpha * (s - shift * ey);
+    if (a.Z) v -= beta * ez;
+    a.out[(long)b * n * KB + (long)erow * KB + tid % KB] = v;
+  }
+  cluster_sync_all();  // the peers' shared memory stays alive until every CTA has read it
 }
 
 // (A persistent variant that walked a whole Chebyshev filter in one cooperative launch - grid barrier on a monotonic

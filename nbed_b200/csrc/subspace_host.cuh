@@ -199,10 +199,13 @@ static void sub_init_cold(nbd_ctx* c) {
   ++c->sub_cold_starts;
 }
 
+// pdl: this product directly follows another product of the same chain in the stream (filter steps 2 .. degree and the
+// Rayleigh-Ritz product behind a filter): it may start while that one is still running (sub_apply3_kernel<KB, 1>).
 template <int KB>
 static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double* Z, double* out, const double* alpha,
-                      const double* shift, const double* beta, int ns) {
+                      const double* shift, const double* beta, int ns, bool pdl = false) {
   const int n = c->nao;
+  pdl = pdl && c->sub_pdl;
   SubApplyArgs a{};
   a.A = A; a.Y = Y; a.Z = Z; a.out = out;
   a.n = n;
@@ -211,25 +214,67 @@ static void sub_apply(nbd_ctx* c, const double* A, const double* Y, const double
     const int q = b < ns ? b : 0;
     a.alpha[b] = alpha[q]; a.shift[b] = shift[q]; a.beta[b] = beta[q];
   }
-  if (c->sub_apply_variant == 0) {
+  // Kernel choice (tools/sub_apply_bench.cu on B200, profiles/r02y_sub_apply_bench.md): the single-shot kernel wins when
+  // its whole grid is resident at once - one spin at n = 1376 (7.6 against 9.8 us per product), both spins at n = 688 -
+  // the ring kernel otherwise (both spins at n = 1376: 10.2 against 14.0 us) and on small matrices.
+  const int smem3 = sub_apply3_smem_bytes<KB>(n);
+  const long ctas3 = (long)((n + SUB3_ROWS - 1) / SUB3_ROWS) * SUB3_KS * ns;
+  const bool fits3 = (n & 1) == 0 && n >= 512 && smem3 <= 200 * 1024 &&
+                     ctas3 <= (long)c->sm_count * ((227 * 1024) / (smem3 + 1024));
+  if (c->sub_apply_variant == 2 || (c->sub_apply_variant == 0 && fits3)) {
+    NBD_REQUIRE((n & 1) == 0 && smem3 <= 200 * 1024, NBD_ERR_ARG, "sub_apply_variant = 2 needs an even nao that fits shared memory");
+    // single-shot bulk-copy kernel: 8-CTA clusters split the contraction index, whole operand slab resident
+    static unsigned long long configured3 = 0;
+    if (first_use_on_current_device(configured3)) {
+      NBD_CUDA(cudaFuncSetAttribute(sub_apply3_kernel<KB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      NBD_CUDA(cudaFuncSetAttribute(sub_apply3_kernel<KB, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      NBD_CUDA(cudaFuncSetAttribute(sub_apply3_kernel<KB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      NBD_CUDA(cudaFuncSetAttribute(sub_apply3_kernel<KB, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((n + SUB3_ROWS - 1) / SUB3_ROWS, SUB3_KS, ns);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem3;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = SUB3_KS;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 2 : 1;
+    if (pdl) NBD_CUDA(cudaLaunchKernelEx(&cfg, sub_apply3_kernel<KB, 1>, a));
+    else NBD_CUDA(cudaLaunchKernelEx(&cfg, sub_apply3_kernel<KB, 0>, a));
+    LAUNCH_CHECK(c);
+    ++c->sub_applies;
+    return;
+  }
+  if (c->sub_apply_variant != 1) {  // 0 (shape does not suit the single-shot kernel) or 3 (forced)
     // cluster split-K kernel: 32 rows per CTA, 4 CTAs of a cluster share the contraction index, DSMEM reduction
     constexpr int smem2 = sub_apply2_smem_bytes<KB>();
     static unsigned long long configured2 = 0;
-    if (first_use_on_current_device(configured2))
-      NBD_CUDA(cudaFuncSetAttribute(sub_apply2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    if (first_use_on_current_device(configured2)) {
+      NBD_CUDA(cudaFuncSetAttribute(sub_apply2_kernel<KB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      NBD_CUDA(cudaFuncSetAttribute(sub_apply2_kernel<KB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((n + SUB2_ROWS - 1) / SUB2_ROWS, SUB2_KS, ns);
     cfg.blockDim = dim3(128);
     cfg.dynamicSmemBytes = smem2;
     cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = SUB2_KS;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    NBD_CUDA(cudaLaunchKernelEx(&cfg, sub_apply2_kernel<KB>, a));
+    cfg.numAttrs = pdl ? 2 : 1;
+    if (pdl) NBD_CUDA(cudaLaunchKernelEx(&cfg, (sub_apply2_kernel<KB, 1>), a));
+    else NBD_CUDA(cudaLaunchKernelEx(&cfg, (sub_apply2_kernel<KB, 0>), a));
     LAUNCH_CHECK(c);
     ++c->sub_applies;
     return;
@@ -309,11 +354,11 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp_all, int s0, int ns) {
       cur = bufs[degree % 3];
       for (int i = 1; i <= degree; ++i) {
         double ai[2] = {alv[0][i], alv[1][i]}, bi[2] = {bev[0][i], bev[1][i]};
-        sub_apply<KB>(c, Fp, bufs[(i - 1) % 3], i >= 2 ? bufs[(i - 2) % 3] : nullptr, bufs[i % 3], ai, cc, i >= 2 ? bi : zero, ns);
+        sub_apply<KB>(c, Fp, bufs[(i - 1) % 3], i >= 2 ? bufs[(i - 2) % 3] : nullptr, bufs[i % 3], ai, cc, i >= 2 ? bi : zero, ns, i >= 2);
       }
     }
     // W = F' Y ; G = Y^T Y, H = Y^T W ; host Rayleigh-Ritz ; V = Y M, AV = W M, residuals
-    sub_apply<KB>(c, Fp, cur, nullptr, sW, one, zero, zero, ns);
+    sub_apply<KB>(c, Fp, cur, nullptr, sW, one, zero, zero, ns, outer > 0);
     sub_gram_kernel<KB><<<dim3(NBLK, ns), 256, 0, c->stream>>>(cur, sW, sGpart, sG, ticket, n);
     LAUNCH_CHECK(c);
     const double* G = d2h_small(c, 0, sG, (size_t)ns * 2 * KB * KB);

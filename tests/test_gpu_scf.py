@@ -363,18 +363,22 @@ def test_huzinaga_embed_overwrites_virtuals_like_the_driver(ctx):
     assert np.abs(v_emb - (h0 + p.v_emb)).max() < 1e-7 and mf.converged == conv0
 
 
-@pytest.mark.parametrize("n,nocc", [(320, 6), (333, 14)])
+@pytest.mark.parametrize("n,nocc", [(320, 6), (333, 14), (544, 5), (530, 12)])
 def test_cluster_split_k_block_product_matches_the_single_cta_kernel(ctx, n, nocc):
-    """sub_apply2_kernel (4-CTA clusters share the contraction index, DSMEM reduction; the default) against the
-    one-CTA-per-16-rows kernel: same iterates, no fallback to the library eigensolver, no rejected run.  n = 333 is odd
-    (8-byte copy path, ragged last row block and chunk) with a 32-vector block."""
+    """The block-product kernels of the subspace eigensolver against each other - 0: automatic choice (the single-shot
+    8-CTA-cluster bulk-copy kernel from n = 512 when its grid is resident at once, else the 4-CTA-cluster ring kernel),
+    1: one CTA per 16 rows, 2 / 3: the two cluster kernels forced, and programmatic dependent launch switched off: same
+    iterates, no fallback to the library eigensolver, no rejected run.  n = 333 is odd (8-byte copy path, ragged last
+    row block and chunk; the single-shot kernel needs an even n) with a 32-vector block; n = 530 has a ragged last row
+    block and a contraction tail that is not a multiple of 4."""
     naux, n_env = 24, 10
     p = syn.make_problem(n=n, naux=naux, nocc=nocc, n_env=n_env, seed=5, scale=3.0 / np.sqrt(n * naux))
     ctx.load_cderi(p.cderi())
     runs = {}
     try:
-        for variant in (0, 1):
-            ctx.set_option("sub_apply_variant", variant)
+        for variant in (0, 1, 3, 4) + ((2,) if n % 2 == 0 else ()):
+            ctx.set_option("sub_apply_variant", variant % 4)
+            ctx.set_option("sub_pdl", 0 if variant == 4 else 1)
             ctx.scf_setup(p.nelec, p.ovlp, p.hcore, p.v_emb, p.dm_enviro, NBD_HUZINAGA)
             f0, r0, a0 = (ctx.timer_ms(k) for k in ("count:sub_fallbacks", "count:sub_rejects", "count:sub_applies"))
             runs[variant] = ctx.huzinaga_scf(30, 1e-8, 1e-6, True)
@@ -382,10 +386,12 @@ def test_cluster_split_k_block_product_matches_the_single_cta_kernel(ctx, n, noc
             assert ctx.timer_ms("count:sub_applies") > a0
     finally:
         ctx.set_option("sub_apply_variant", 0)
-    a, b = runs[0], runs[1]
-    assert a[4]["cycles"] == b[4]["cycles"] and a[4]["converged"] == b[4]["converged"]
-    assert np.abs(a[4]["trace"] - b[4]["trace"]).max() < 1e-9
-    assert np.abs(a[2] - b[2]).max() < 1e-9 and np.abs(a[1] - b[1]).max() < 1e-8
+        ctx.set_option("sub_pdl", 1)
+    a = runs[0]
+    for variant, b in runs.items():
+        assert a[4]["cycles"] == b[4]["cycles"] and a[4]["converged"] == b[4]["converged"], variant
+        assert np.abs(a[4]["trace"] - b[4]["trace"]).max() < 1e-9, variant
+        assert np.abs(a[2] - b[2]).max() < 1e-9 and np.abs(a[1] - b[1]).max() < 1e-8, variant
     # and against the oracle's full diagonalisation in every cycle
     mf = ps.DFUHF(p.ovlp, p.hcore, p.cderi(), p.nelec, max_cycle=30, conv_tol=1e-8)
     _, e0, d0, _, conv0 = nr.huzinaga_scf(mf, p.v_emb, p.dm_enviro)
