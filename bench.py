@@ -34,6 +34,8 @@ WORKLOADS = {
     "C4o20": ("C4_h2o32_def2tzvp_o20", "synthetic (H2O)32/def2-TZVP-shaped, 20 active occupied per spin (n=1376, naux=4128, UHF): tensor-bound regime"),
     "C5": ("C5_h2o16_def2tzvp", "synthetic (H2O)16/def2-TZVP-shaped (n=688, naux=2064, o=5/spin, UHF)"),
     "C3": ("C3_ethanol_ccpvtz", "synthetic ethanol/cc-pVTZ-shaped (n=174, naux=522, o=9/spin, UHF)"),
+    "C2": ("C2_h2o_ccpvdz", "synthetic H2O/cc-pVDZ-shaped (n=24, naux=72, o=4/spin, UHF)"),
+    "C1": ("C1_h2o_sto3g", "synthetic H2O/STO-3G-shaped (n=7, naux=21, o=4/spin, UHF)"),
 }
 
 

@@ -22,6 +22,7 @@
 #include "scf_kernels.cuh"
 #include "integrals.cuh"
 #include "subspace.cuh"
+#include "small_eigh.cuh"
 
 using namespace nbd;
 
@@ -145,6 +146,7 @@ struct nbd_ctx {
   cudaEvent_t ev_export = nullptr;
   PinnedBuf pinned2;
   int overlap = 1;
+  int small_eigh = 1;   // n <= 32: one-CTA Jacobi eigensolver (small_eigh.cuh) instead of cuSOLVER dsyevd
   int eig_threads = 1;  // second spin's full eigensolve issued from a helper thread on the side stream
   int dist_eig = 1;
   int ks_energy = 0;  // mu / kernel() path with XC on: 1 = pyscf's KS energy_elec (e1 + ecoul + exc), 0 = nbed's patched energy_elec (e1 + tr(vhf D) / 2)
@@ -697,6 +699,15 @@ static void eig_exchange(nbd_ctx* c, double* A, double* w, int n) {
 }
 
 static void eigh_batched(nbd_ctx* c, double* A, double* w, int n, int batch) {
+  if (n <= SE_MAX_N && c->small_eigh) {
+    // one launch per batch instead of cuSOLVER's chain of tiny ones (0.1-0.2 ms per matrix at n = 7 / 24)
+    int* info = c->devinfo.ensure(8);
+    NBD_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 8, c->stream));
+    StageScope ts(c->timers, c->stream, "eigh");
+    small_eigh_kernel<<<batch, SE_THREADS, 0, c->stream>>>(A, w, n);
+    LAUNCH_CHECK(c);
+    return;
+  }
   int lwork = 0;
   // numpy.linalg.eigh reads the lower triangle of the row-major matrix == the UPPER triangle column-major
   NBD_SOLVER(cusolverDnDsyevd_bufferSize(c->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A, n, w, &lwork));
@@ -942,6 +953,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "timers") c->timers.enabled = value != 0;
   else if (k == "overlap") c->overlap = (int)value;
   else if (k == "eig_threads") c->eig_threads = (int)value;
+  else if (k == "small_eigh") c->small_eigh = (int)value;
   else if (k == "dist_eig") c->dist_eig = (int)value;
   else if (k == "dist_orth") c->dist_orth = (int)value;
   else if (k == "ks_energy") c->ks_energy = (int)value;
