@@ -562,10 +562,21 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
                                                                 double* __restrict__ part, int ntiles, int naux,
                                                                 int nsplit, int rows_per_split,
                                                                 unsigned int* __restrict__ next_item, int sm_mod,
-                                                                int sm_keep, int nst) {
+                                                                int sm_keep, int nst, int guests = 0, long guest_limit = 0) {
   // spatial split of the pair (pass 2 on some SMs, the K Gram on the others): CTAs that land on an SM of the other
-  // group retire at once; the dynamic item queue hands all the work to the CTAs that stay
-  if (sm_mod > 0 && !sm_in_group1(smid(), sm_keep, sm_mod)) return;  // sm_keep of the sm_mod SMs run pass 2
+  // group retire at once; the dynamic item queue hands all the work to the CTAs that stay.
+  // guests > 0: the first `guests` CTAs that land on a Gram SM stay as well (next_item[1 + smid] counts them).  Next to
+  // the Gram's DMMA warps they stream at a fraction of the normal rate, but that is bandwidth the pair would otherwise
+  // not use; they stop drawing items at `guest_limit` so that a slow guest never holds the last items of the queue.
+  bool guest = false;
+  if (sm_mod > 0 && !sm_in_group1(smid(), sm_keep, sm_mod)) {  // sm_keep of the sm_mod SMs run pass 2
+    if (guests <= 0) return;
+    __shared__ unsigned int s_guest;
+    if (threadIdx.x == 0) s_guest = atomicAdd(next_item + 1 + smid(), 1u);
+    __syncthreads();
+    if (s_guest >= (unsigned int)guests) return;
+    guest = true;
+  }
   extern __shared__ __align__(128) unsigned char jsm[];
   // ring depth nst <= JP_MAX_STAGES is a launch parameter: 7 next to the Gram, 9 when pass 2 has its SMs to itself
   uint64_t* full = reinterpret_cast<uint64_t*>(jsm);
@@ -592,7 +603,9 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
       bool first = true;
       const uint64_t pol = l2_evict_first_policy();
       for (unsigned int seq = 0;; ++seq) {
-        long item = (long)atomicAdd(next_item, 1u);
+        long item;
+        if (guest && (long)*reinterpret_cast<volatile unsigned int*>(next_item) >= guest_limit) item = -1;
+        else item = (long)atomicAdd(next_item, 1u);
         if (item >= nitems) item = -1;
         if (!first) mbar_wait(&empty[st], ph);  // (also guarantees the consumers are done with item_q[seq & 15])
         item_q[seq & 15] = item;

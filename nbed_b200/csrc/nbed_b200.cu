@@ -162,6 +162,8 @@ struct nbd_ctx {
   int syrk_ctas = 0;      // CTAs of that kernel (0 = one per SM)
   DBuf<double> syrk_ws;   // its partial tiles
   DBuf<unsigned int> d_syrk_counter;
+  int pair_guest_reserve = 30;  // guests leave the last 1 / pair_guest_reserve of the item queue alone (3 / 6 / 12 / 30 measured: 5.85 / 5.83 / 5.75 / 5.73 ms)
+  int pair_guest = 1;     // pass-2 CTAs that stay on every Gram SM of the split pair (0 / 1 / 2 measured: pass 2 6.04-6.10 / 5.73-5.83 / 5.81 ms, profiles/r02_pair_split.md)
   int pair_split = -1;    // > 0: pass 2 runs on this many SMs (3 CTAs each), the stream-K Gram on the others; 0: both everywhere; -1: automatic
   int jpass_variant = 0;  // 0: TMA-fed persistent pass 2, 1: LDG streaming pass 2
   int panel_stages = 0;  // tuning: cap on the ring depth of the panel kernel (0 = as many as fit)
@@ -491,8 +493,9 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
       int nsplit = (int)std::max<long>(1, std::min<long>(std::min(naux, 16), (16L * ctas + c->ntiles - 1) / c->ntiles));
       const int rows_per_split = (naux + nsplit - 1) / nsplit;
       nsplit = (naux + rows_per_split - 1) / rows_per_split;
-      unsigned int* counter = c->d_jcounter.ensure(4);
+      unsigned int* counter = c->d_jcounter.ensure(4 + 512);  // [0] item queue, [1 + smid] guest CTAs per SM
       const int nst = p2 > 0 ? JP_STAGES_ALONE : JP_STAGES;
+      const int guests = p2 > 0 ? c->pair_guest : 0;
       const size_t smem = JP_HEADER + (size_t)nst * TILE_BYTES, smem_max = JP_HEADER + (size_t)JP_MAX_STAGES * TILE_BYTES;
       static unsigned long long configured = 0;
       if (first_use_on_current_device(configured)) {
@@ -506,7 +509,9 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
         const int ns = std::min(2, njset - s0);
         double* part = c->d_jpart.ensure((size_t)nsplit * ns * E);
         const int grid = (int)std::min<long>((long)c->ntiles * nsplit, ctas);
-        NBD_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+        NBD_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * (4 + 512), st));
+        // guests leave the last sixth of the queue to the CTAs that own their SM
+        const long glimit = (long)c->ntiles * nsplit - (long)c->ntiles * nsplit / std::max(2, c->pair_guest_reserve);
         if (!c->jpass_safe) {  // legacy release order (experiments only)
           NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
           NBD_CUDA(cudaFuncSetAttribute(j_pass_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
@@ -515,9 +520,9 @@ static void jk_device(nbd_ctx* c, const double* d_orb, const double* d_wt, int N
           else
             j_pass_tma_kernel<1, false><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter, sm_mod, sm_keep, nst);
         } else if (ns == 2)
-          j_pass_tma_kernel<2><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter, sm_mod, sm_keep, nst);
+          j_pass_tma_kernel<2><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter, sm_mod, sm_keep, nst, guests, glimit);
         else
-          j_pass_tma_kernel<1><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter, sm_mod, sm_keep, nst);
+          j_pass_tma_kernel<1><<<grid, JP_THREADS, smem, st>>>(c->Bt, rho + (long)s0 * naux, part, c->ntiles, naux, nsplit, rows_per_split, counter, sm_mod, sm_keep, nst, guests, glimit);
         LAUNCH_CHECK(c);
         if (behind && s0 == 0) behind();
         j_finalize_kernel<<<gf, 128, 0, st>>>(part, c->d_inv.p, d_J + (long)s0 * nn, n, c->nb, E, nsplit, ns);
@@ -963,6 +968,8 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "gemm_tile") c->gemm_tile = (int)value;
   else if (k == "syrk") c->syrk_mode = (int)value;
   else if (k == "pair_split") c->pair_split = (int)value;
+  else if (k == "pair_guest") c->pair_guest = (int)value;
+  else if (k == "pair_guest_reserve") c->pair_guest_reserve = (int)value;
   else if (k == "jpass_safe") c->jpass_safe = (int)value;
   else if (k == "copy_threads") g_copy_threads = (int)value;
   else if (k == "x_cache") { if (c->x_cache != (int)value) c->x_valid_n = 0; c->x_cache = (int)value; }
