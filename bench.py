@@ -70,14 +70,20 @@ FP64_PEAK_TFLOPS = 37.2  # profiles/microbench_r01.md: DMMA m8n8k4 measured on t
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md): `nvidia-smi -lms 100` is the
+    primary source; because the timed region of the default run is only ~0.3 s and nvidia-smi sometimes needs more than
+    a second to deliver its first line, an NVML poller (the library nvidia-smi itself reads, 20 ms period) runs next to
+    it and is used when nvidia-smi put fewer than two samples inside the region."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.rows = []
+        self.nvml_rows = []
         self.proc = None
+        self._stop = False
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
@@ -86,33 +92,62 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        self.t2 = threading.Thread(target=self._poll_nvml, args=(index,), daemon=True)
+        self.t2.start()
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
+    def _poll_nvml(self, index):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = get_reasons(h)
+                self.nvml_rows.append((time.perf_counter(), float(sm), float(smax), [k for k, b in bits.items() if r & b]))
+                time.sleep(0.02)
+        except Exception:
+            pass
+
+    def wait_ready(self, timeout=4.0):
+        """Block (before the timed region) until a source has delivered its first sample."""
+        t_end = time.perf_counter() + timeout
+        while time.perf_counter() < t_end and not self.rows and not self.nvml_rows:
+            time.sleep(0.02)
+
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, smax, reasons, source = [], None, set(), "nvidia-smi"
         inside = [r for r in self.rows if t0 <= r[0] <= t1 + 0.2]
-        # a timed region shorter than the sampling period: fall back to the samples under load around it
-        rows = inside if len(inside) >= 2 else [r for r in self.rows if t0 - 1.0 <= r[0] <= t1 + 0.5]
-        for ts, line in rows:
+        for ts, line in inside:
             f = [x.strip() for x in line.split(",")]
             try:
                 sm.append(float(f[0]))
                 smax = float(f[1])
             except Exception:
                 continue
-            for nm, v in zip(names, f[3:7]):
+            for nm, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        if len(sm) < 2:  # nvidia-smi was late or the region shorter than its period: the NVML poller's samples inside it
+            rows = [r for r in self.nvml_rows if t0 <= r[0] <= t1]
+            if len(rows) >= 2:
+                sm, smax, reasons, source = [r[1] for r in rows], rows[0][2], set(x for r in rows for x in r[3]), "nvml"
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock samples (nvidia-smi and NVML unavailable)"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "samples": len(sm), "reasons": sorted(reasons), "source": source}
 
 
 # Coupling strength of the synthetic 3-centre tensor (multiples of 1/sqrt(naux * nao)): chosen so that the embedded
@@ -303,6 +338,8 @@ def run_b200(args):
         e, nd = ctx.scf_bench_iteration(it)
         log(f"warm-up iteration {it}: {ctx.timer_ms('iter_total'):.2f} ms E={e} |dD|={nd:.3e} {ctx.timers()}")
         it += 1
+    if sampler:
+        sampler.wait_ready()  # never start the (0.3 s) timed region before the clock sampler delivers
     stage_keys = ("jk_x", "jk_rho", "jk_k", "jk_j", "jk_total", "allreduce", "fock", "diis", "orth", "orth_gather", "eigh", "eig_sub",
                   "eig_bcast", "density", "energy", "iter_total")
     stages = {k: 0.0 for k in stage_keys}
