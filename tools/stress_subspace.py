@@ -7,9 +7,10 @@ from oracle import nbed_restatement as nr, pyscf_restatement as ps
 ctx = B200Context(0)
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 ncase = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+nlo, nhi = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (256, 420)  # 512+ reaches the single-shot block product
 bad = 0; worst_e = worst_d = 0.0
 for case in range(ncase):
-    n = int(rng.integers(256, 420)); naux = int(rng.integers(8, 40)); nocc = int(rng.integers(1, 22))
+    n = int(rng.integers(nlo, nhi)); naux = int(rng.integers(8, 40)); nocc = int(rng.integers(1, 22))
     n_env = int(rng.integers(1, 30)); scale = float(rng.uniform(1.0, 5.0)); diis = bool(rng.integers(0, 4))
     p = syn.make_problem(n=n, naux=naux, nocc=nocc, n_env=n_env, seed=int(rng.integers(0, 1000)), scale=scale / np.sqrt(n * naux))
     b = p.cderi(); ctx.load_cderi(b)
