@@ -50,7 +50,12 @@ int nbd_set_option(nbd_ctx* ctx, const char* key, long value);
  * "overlap" (0 = pass 2 behind the K Gram, 1 = side stream, 3 = same stream with programmatic dependent launch),
  * "sub_bound" (1 = Lanczos + ||dF||_F spectral bounds, 0 = row sums), "sub_cold" (1 = initial guess by cold-start
  * subspace iteration, 0 = cuSOLVER), "dist_eig", "panel_stages", "panel_hybrid" (1 = 9-10 column slices run 8 columns on DMMA + 1-2 on the
- * FMA pipe, 0 = padded to 16 DMMA columns), "x_budget_mb", "timers". */
+ * FMA pipe, 0 = padded to 16 DMMA columns), "x_budget_mb", "timers"; round 2: "sub_apply_variant" (block product of the
+ * subspace eigensolver: 0 = automatic, 1 = one CTA per 16 rows, 2 = single-shot 8-CTA-cluster kernel, 3 = 4-CTA-cluster
+ * ring kernel), "sub_pdl" (1 = consecutive block products overlap through programmatic dependent launch), "pair_split"
+ * (pass-2 SMs of the pair [pass 2 || K Gram]; -1 = automatic), "pair_guest" (pass-2 guest CTAs per Gram SM),
+ * "pair_guest_reserve", "small_eigh" (1 = one-CTA Jacobi eigensolver for nao <= 32, 0 = cuSOLVER), "early_export"
+ * (1 = nbd_huzinaga_scf copies D / Huz out while the final eigensolve runs), "x_cache", "copy_threads". */
 double nbd_timer_ms(nbd_ctx* ctx, const char* key);
 /* Number of kernels launched by this library since the context was created (bench "gpu_launches"). */
 long nbd_launch_count(nbd_ctx* ctx);
