@@ -146,6 +146,10 @@ struct nbd_ctx {
   cudaEvent_t ev_export = nullptr;
   PinnedBuf pinned2;
   int overlap = 1;
+  int small_eigh_warm = 1;  // ... started from the previous SCF cycle's eigenvectors
+  DBuf<double> seWarm;
+  int se_warm_n = 0, se_warm_batch = 0;
+  long se_warm_calls = 0;  // solves since the warm basis was last reset (0 = none valid)
   int small_eigh = 1;   // n <= 32: one-CTA Jacobi eigensolver (small_eigh.cuh) instead of cuSOLVER dsyevd
   int eig_threads = 1;  // second spin's full eigensolve issued from a helper thread on the side stream
   int dist_eig = 1;
@@ -703,13 +707,26 @@ static void eig_exchange(nbd_ctx* c, double* A, double* w, int n) {
   if (r != ncclSuccess) fail(NBD_ERR_CUDA, "ncclBroadcast (eigenvectors): %s", g_nccl.GetErrorString(r));
 }
 
-static void eigh_batched(nbd_ctx* c, double* A, double* w, int n, int batch) {
+// warm_slot = 1: the Fock matrix of the SCF loop - the eigenvectors of the previous cycle (kept in c->seWarm while
+// c->se_warm_calls > 0) are the starting basis of the small-matrix Jacobi solver; every 16th solve starts from the
+// identity again so that the accumulated rotations cannot drift away from orthogonality.
+static void eigh_batched(nbd_ctx* c, double* A, double* w, int n, int batch, int warm_slot = 0) {
   if (n <= SE_MAX_N && c->small_eigh) {
     // one launch per batch instead of cuSOLVER's chain of tiny ones (0.1-0.2 ms per matrix at n = 7 / 24)
     int* info = c->devinfo.ensure(8);
     NBD_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 8, c->stream));
     StageScope ts(c->timers, c->stream, "eigh");
-    small_eigh_kernel<<<batch, SE_THREADS, 0, c->stream>>>(A, w, n);
+    double* warm = nullptr;
+    int use = 0;
+    if (warm_slot == 1 && c->small_eigh_warm && batch <= 2) {
+      warm = c->seWarm.ensure((size_t)2 * SE_MAX_N * SE_MAX_N);
+      use = (c->se_warm_n == n && c->se_warm_batch == batch && c->se_warm_calls > 0 && c->se_warm_calls % 16 != 0) ? 1 : 0;
+      if (c->se_warm_n != n || c->se_warm_batch != batch) c->se_warm_calls = 0;
+      c->se_warm_n = n;
+      c->se_warm_batch = batch;
+      ++c->se_warm_calls;
+    }
+    small_eigh_kernel<<<batch, SE_THREADS, 0, c->stream>>>(A, w, n, warm, use);
     LAUNCH_CHECK(c);
     return;
   }
@@ -959,6 +976,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "overlap") c->overlap = (int)value;
   else if (k == "eig_threads") c->eig_threads = (int)value;
   else if (k == "small_eigh") c->small_eigh = (int)value;
+  else if (k == "small_eigh_warm") { c->small_eigh_warm = (int)value; c->se_warm_calls = 0; }
   else if (k == "dist_eig") c->dist_eig = (int)value;
   else if (k == "dist_orth") c->dist_orth = (int)value;
   else if (k == "ks_energy") c->ks_energy = (int)value;

@@ -171,7 +171,7 @@ static void scf_diagonalise_lowdin(nbd_ctx* c, bool allow_subspace = false, bool
     }
     ++c->sub_fallbacks;  // not converged: fall through to the library eigensolver on the same F'
   }
-  eigh_batched(c, c->T2.p, c->evals.p, n, c->nspin);
+  eigh_batched(c, c->T2.p, c->evals.p, n, c->nspin, /*warm_slot=*/1);
   {
     StageScope ts(c->timers, c->stream, "orth");
     gemm_nn(c, n, n, n, c->T2.p, n, c->Xh.p, n, c->Ct.p, n, 1.0, 0.0, c->nspin, nn, 0, nn);
@@ -344,6 +344,7 @@ extern "C" int nbd_scf_setup(nbd_ctx* c, int nspin, const int* nelec, const doub
     }
     LAUNCH_CHECK(c);
     c->scf_ready = true;
+    c->se_warm_calls = 0;  // the small-matrix eigensolver's warm basis never survives a change of problem
     c->bench_ready = false;
     c->have_virt = false;
     c->env_rank = 0;
@@ -425,6 +426,7 @@ static void huz_initial(nbd_ctx* c, const double* dm0, HuzLoop& L) {
   c->sub_valid = false;  // a new SCF never inherits the eigenvector block or the spectral bounds of the last one
   c->sub_bounds_valid = false;
   c->sub_rate = 0.0;
+  c->se_warm_calls = 0;  // ... nor the warm basis of the small-matrix eigensolver (repeated runs stay bit-identical)
   if (!dm0) {
     NBD_CUDA(cudaMemcpyAsync(c->F.p, c->heff.p, sizeof(double) * nn * c->nspin, cudaMemcpyDeviceToDevice, c->stream));
     scf_apply_huzinaga(c);

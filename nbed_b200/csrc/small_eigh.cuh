@@ -16,9 +16,15 @@ namespace nbd {
 constexpr int SE_MAX_N = 32;
 constexpr int SE_THREADS = 256;  // 8 warps: warp w owns the pairs w and w + 8 of a round, lane = row / column index
 
-__global__ void __launch_bounds__(SE_THREADS) small_eigh_kernel(double* __restrict__ Aall, double* __restrict__ wall, int n) {
+// warm (optional): [batch][n][n] eigenvector rows of the PREVIOUS solve of a slowly changing matrix (the Fock matrix of
+// consecutive SCF cycles).  With use_warm the kernel first rotates A into that basis (A' = E A E^T, nearly diagonal), so
+// the sweeps start a few orders of magnitude closer to convergence, and accumulates its rotations on E^T instead of the
+// identity; the result is the same decomposition of A.  The new eigenvector rows are always written back to `warm`.
+__global__ void __launch_bounds__(SE_THREADS) small_eigh_kernel(double* __restrict__ Aall, double* __restrict__ wall, int n,
+                                                                double* __restrict__ warm = nullptr, int use_warm = 0) {
   __shared__ double A[SE_MAX_N][SE_MAX_N + 1];
   __shared__ double V[SE_MAX_N][SE_MAX_N + 1];
+  __shared__ double T[SE_MAX_N][SE_MAX_N + 1];
   __shared__ double red[SE_THREADS / 32][2];
   __shared__ double norms[2];
   __shared__ int rank_of[SE_MAX_N];
@@ -32,6 +38,33 @@ __global__ void __launch_bounds__(SE_THREADS) small_eigh_kernel(double* __restri
     V[i][j] = i == j ? 1.0 : 0.0;
   }
   __syncthreads();
+  if (warm != nullptr && use_warm) {
+    const double* E = warm + (long)blockIdx.x * n * n;
+    for (int e = tid; e < SE_MAX_N * SE_MAX_N; e += SE_THREADS) {
+      const int i = e >> 5, k = e & 31;
+      V[i][k] = (i < n && k < n) ? E[(long)k * n + i] : (i == k ? 1.0 : 0.0);  // columns of V = previous eigenvectors
+    }
+    __syncthreads();
+    for (int e = tid; e < SE_MAX_N * SE_MAX_N; e += SE_THREADS) {  // T = A V
+      const int i = e >> 5, k = e & 31;
+      double t = 0.0;
+      for (int j = 0; j < n; ++j) t = fma(A[i][j], V[j][k], t);
+      T[i][k] = t;
+    }
+    __syncthreads();
+    for (int e = tid; e < SE_MAX_N * SE_MAX_N; e += SE_THREADS) {  // A' = V^T T, symmetrised
+      const int k = e >> 5, l = e & 31;
+      if (k < n && l < n && l <= k) {
+        double t = 0.0, u = 0.0;
+        for (int i = 0; i < n; ++i) {
+          t = fma(V[i][k], T[i][l], t);
+          u = fma(V[i][l], T[i][k], u);
+        }
+        A[k][l] = A[l][k] = 0.5 * (t + u);
+      }
+    }
+    __syncthreads();
+  }
   const int m = (n + 1) & ~1;  // players of the tournament (index n = a bye when n is odd)
   const int npair = m / 2;
   for (int sweep = 0; sweep < 40; ++sweep) {
@@ -147,6 +180,7 @@ __global__ void __launch_bounds__(SE_THREADS) small_eigh_kernel(double* __restri
   for (int e = tid; e < n * n; e += SE_THREADS) {
     const int k = e / n, i = e % n;  // eigenvector k (column k of V), component i
     Ag[(long)rank_of[k] * n + i] = V[i][k];
+    if (warm != nullptr) warm[(long)blockIdx.x * n * n + (long)rank_of[k] * n + i] = V[i][k];
   }
 }
 
