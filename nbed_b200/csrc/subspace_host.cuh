@@ -397,6 +397,7 @@ static bool sub_solve_t(nbd_ctx* c, const double* Fp_all, int s0, int ns) {
       }
     }
     ++c->sub_outer;
+    if (getenv("NBD_SUB_DEBUG")) fprintf(stderr, "[sub] s0=%d ns=%d outer=%d cold=%d degree=%d worst=%.3e rate=%.4f\n", s0, ns, outer, (int)cold, outer > 0 ? deg_prev : 0, worst, c->sub_rate);
     cur = c->sV.p + s0 * blk;
     if (worst < tol) return true;
     if (!cold && outer > 0 && deg_prev > 0 && worst_prev > 0.0 && worst < worst_prev)
