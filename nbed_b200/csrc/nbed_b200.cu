@@ -195,6 +195,8 @@ struct nbd_ctx {
   PinnedBuf rb;  // small read-backs of the SCF loop (subspace_host.cuh: d2h_small)
 
   // ---- J/K workspaces ----
+  DBuf<double> d_jkpack;  // packed lower triangles of [J | K sets] (multi-GPU all-reduce buffer of the SCF loop)
+  int packed_allreduce = 1;
   DBuf<double> d_orb, d_wt, d_X, d_rho, d_jpart, d_jk;  // d_jk = [J sets | K sets] contiguous (all-reduce buffer)
   DBuf<int> d_setbegin;
   std::map<int, PlanDev> plans;  // device copies of the panel kernel's task lists, keyed by ring depth
@@ -992,6 +994,7 @@ int nbd_set_option(nbd_ctx* c, const char* key, long value) {
   else if (k == "copy_threads") g_copy_threads = (int)value;
   else if (k == "x_cache") { if (c->x_cache != (int)value) c->x_valid_n = 0; c->x_cache = (int)value; }
   else if (k == "early_export") c->early_export = (int)value;
+  else if (k == "packed_allreduce") c->packed_allreduce = (int)value;
   else if (k == "jpass_sm_mod") c->jpass_sm_mod = (int)value;
   else if (k == "jpass_sm_keep") c->jpass_sm_keep = (int)value;
   else if (k == "jpass_ctas_per_sm") c->jpass_ctas_per_sm = (int)value;

@@ -35,11 +35,27 @@ static void scf_build_fock(nbd_ctx* c, int Ntot, const std::vector<KGroup>& grou
   double* buf = c->d_jk.ensure((size_t)(1 + ns) * nn);
   std::vector<int> jbegin = {0, Ntot};
   jk_device(c, c->d_orb.p, c->d_wt.p, Ntot, 1, jbegin, buf, ns, groups, buf + nn);
+  // UHF: J - K_s; RHF: J - K / 2; UKS: J - hyb K_s; RKS: J - hyb K / 2   (pyscf/dft/{uks,rks}.py:get_veff)
+  const double kscale = (ks ? c->xc.hyb : 1.0) * (ns == 2 ? 1.0 : 0.5);
+  if (c->world > 1 && c->comm && c->packed_allreduce && !ks && n >= 256) {
+    // symmetric partial sums: the ranks exchange the lower triangles only (half the all-reduce bytes), and the Fock
+    // assembly reads the packed sums directly.  (Kohn-Sham objects keep the square buffers: their traces read J and K.)
+    const long npack = (long)n * (n + 1) / 2;
+    double* pk = c->d_jkpack.ensure((size_t)(1 + ns) * npack);
+    {
+      StageScope ts(c->timers, c->stream, "allreduce");
+      pack_lower_kernel<<<dim3((n + 127) / 128, n, 1 + ns), 128, 0, c->stream>>>(buf, pk, n, npack);
+      LAUNCH_CHECK(c);
+    }
+    all_reduce(c, pk, (size_t)(1 + ns) * npack);
+    StageScope ts(c->timers, c->stream, "fock");
+    fock_from_heff_packed_kernel<<<dim3((n + 127) / 128, n), 128, 0, c->stream>>>(c->heff.p, pk, kscale, c->F.p, c->vhf.p, n, npack, ns);
+    LAUNCH_CHECK(c);
+    return;
+  }
   all_reduce(c, buf, (size_t)(1 + ns) * nn);
   {
     StageScope ts(c->timers, c->stream, "fock");
-    // UHF: J - K_s; RHF: J - K / 2; UKS: J - hyb K_s; RKS: J - hyb K / 2   (pyscf/dft/{uks,rks}.py:get_veff)
-    const double kscale = (ks ? c->xc.hyb : 1.0) * (ns == 2 ? 1.0 : 0.5);
     fock_from_heff_kernel<<<grid1(nn, 256), 256, 0, c->stream>>>(c->heff.p, buf, buf + nn, kscale, c->F.p, c->vhf.p, nn, ns);
     LAUNCH_CHECK(c);
   }

@@ -181,6 +181,27 @@ __global__ void fock_from_heff_kernel(const double* __restrict__ heff, const dou
   }
 }
 
+// Multi-GPU form of the same step.  J and K are symmetric, so the ranks all-reduce only the lower triangles: the
+// (1 + nspin) matrices are packed row by row ([m][i (i + 1) / 2 + j], j <= i) - 22.7 MB instead of 45.5 MB per Fock
+// build at n = 1376 - and the Fock assembly reads both triangles from the packed sums (no unpacking pass).
+__global__ void pack_lower_kernel(const double* __restrict__ A, double* __restrict__ P, int n, long npack) {
+  const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.z;
+  if (j <= i) P[(long)m * npack + (long)i * (i + 1) / 2 + j] = A[(long)m * n * n + (long)i * n + j];
+}
+__global__ void fock_from_heff_packed_kernel(const double* __restrict__ heff, const double* __restrict__ JKp, double kscale,
+                                             double* __restrict__ F, double* __restrict__ vhf, int n, long npack, int nspin) {
+  const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const long p = i >= j ? (long)i * (i + 1) / 2 + j : (long)j * (j + 1) / 2 + i;
+  const long e = (long)i * n + j, nn = (long)n * n;
+  const double jj = JKp[p];
+  for (int s = 0; s < nspin; ++s) {
+    const double v = jj - kscale * JKp[(long)(1 + s) * npack + p];
+    vhf[(long)s * nn + e] = v;
+    F[(long)s * nn + e] = heff[(long)s * nn + e] + v;
+  }
+}
+
 // Per-spin traces of one SCF cycle in a single pass over the matrices (all symmetric, so sum_ij A_ij D_ji is
 // taken element-wise):  part[blk][4*s + 0..2] = sum a_s.D_s, sum b_s.D_s, sum c_s.D_s ; [4*s+3] = sum (D_s - Dold_s)^2
 // (nbed/scf/huzinaga_scf.py:182-194; nbed/scf/embedded_hcore_funcs.py:38-41).  Null operands are skipped.

@@ -462,3 +462,26 @@ def test_block_product_kernels_against_a_plain_reference(tmp_path):
     out = _run_cuda_tool(tmp_path, "sub_apply_bench", ("334", "2", "20"))
     devs = [float(x) for x in re.findall(r"max\|out - ref\| = ([0-9.e+-]+)", out.stdout)]
     assert out.returncode == 0 and len(devs) == 8 and max(devs) < 1e-13, out.stdout[-800:] + out.stderr[-300:]
+
+
+def test_huzinaga_rhf_subspace_path_with_the_single_shot_block_product(ctx):
+    """Restricted (rank-2) Huzinaga SCF at n = 544: one spin per block-product launch, i.e. the shape in which the
+    single-shot 8-CTA-cluster kernel is chosen on ONE GPU (on >= 2 GPUs the spin split produces it for UHF as well).
+    Iterates against the oracle's full diagonalisation in every cycle."""
+    n, naux, nocc, n_env = 544, 16, 7, 9
+    p = syn.make_problem(n=n, naux=naux, nocc=nocc, n_env=n_env, seed=4, scale=3.0 / np.sqrt(n * naux))
+    b = p.cderi()
+    mf = ps.DFRHF(p.ovlp, p.hcore, b, p.nelec, max_cycle=30, conv_tol=1e-8)
+    tr = []
+    v, g = p.v_emb[0], 2.0 * p.dm_enviro[0]
+    c0, e0, d0, h0, conv0 = nr.huzinaga_scf(mf, v, g, trace=tr)
+    ctx.load_cderi(b)
+    ctx.scf_setup(p.nelec, p.ovlp, p.hcore, v, g, NBD_HUZINAGA)
+    a0, f0, r0 = (ctx.timer_ms(k) for k in ("count:sub_applies", "count:sub_fallbacks", "count:sub_rejects"))
+    c1, e1, d1, h1, info = ctx.huzinaga_scf(30, 1e-8, 1e-6, True)
+    assert ctx.timer_ms("count:sub_applies") > a0 and ctx.timer_ms("count:sub_fallbacks") == f0
+    assert ctx.timer_ms("count:sub_rejects") == r0
+    _same_stop(info, conv0, tr)
+    for k, t in enumerate(tr[: info["cycles"]]):
+        assert abs(info["trace"][k, 0] - float(t["energy"])) < E_TOL, k
+    assert np.abs(d1 - d0).max() < 1e-8 and np.abs(h1 - h0).max() < 1e-7 and np.abs(e1 - e0).max() < 1e-8
