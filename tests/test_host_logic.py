@@ -160,3 +160,56 @@ def test_host_linear_algebra_of_the_scf_drivers(tmp_path):
     subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(exe), src], check=True, timeout=300)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "fails=0" in out.stdout, out.stdout[-800:]
+
+
+def test_result_pool_recycles_page_locked_blocks(monkeypatch):
+    """nbed_b200._lib.result_empty: results of 1 MiB and more live in blocks of nbd_host_alloc that return to a pool when
+    the array AND every view of it have been garbage collected, and are handed out again for the next result of that
+    size; smaller results are plain NumPy arrays; a failed allocation falls back to a pageable array."""
+    import ctypes
+    import gc
+
+    from nbed_b200 import _lib
+
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype, libc.malloc.argtypes, libc.free.argtypes = ctypes.c_void_p, [ctypes.c_size_t], [ctypes.c_void_p]
+
+    class Fake:
+        def __init__(self):
+            self.allocs, self.frees, self.fail = [], [], False
+
+        def nbd_host_alloc(self, n):
+            if self.fail:
+                return None
+            p = libc.malloc(n)
+            self.allocs.append(p)
+            return p
+
+        def nbd_host_free(self, p):
+            self.frees.append(p)
+            libc.free(p)
+
+    fake = Fake()
+    monkeypatch.setattr(_lib, "load", lambda: fake)
+    monkeypatch.setattr(_lib, "_POOL", {})
+    monkeypatch.setattr(_lib, "_POOL_STATE", {"bytes": 0, "cap": 8 << 20})
+    a = _lib.result_empty((512, 512))
+    a[:] = 1.0
+    addr, view = a.ctypes.data, a[:10]
+    del a
+    gc.collect()
+    assert not any(_lib._POOL.values()) and view.sum() == 5120.0  # a view keeps the block out of the pool
+    del view
+    gc.collect()
+    assert sum(len(v) for v in _lib._POOL.values()) == 1 and _lib._POOL_STATE["bytes"] == 512 * 512 * 8
+    b = _lib.result_empty((512, 512))
+    assert b.ctypes.data == addr and len(fake.allocs) == 1 and _lib._POOL_STATE["bytes"] == 0
+    assert len(fake.allocs) == 1 and isinstance(_lib.result_empty((4, 4)), np.ndarray) and len(fake.allocs) == 1
+    big = [_lib.result_empty((1024, 1024)) for _ in range(2)]  # 2 x 8 MiB against a cap of 8 MiB: one is freed for real
+    del big, b
+    gc.collect()
+    assert _lib._POOL_STATE["bytes"] <= 8 << 20 and len(fake.frees) >= 1
+    fake.fail = True
+    c = _lib.result_empty((600, 600))
+    c[:] = 2.0
+    assert c.shape == (600, 600) and c.sum() == 720000.0
