@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(JP_THREADS) j_pass_tma_kernel(const double* __
   if (sm_mod > 0 && !sm_in_group1(smid(), sm_keep, sm_mod)) {  // sm_keep of the sm_mod SMs run pass 2
     if (guests <= 0) return;
     __shared__ unsigned int s_guest;
-    if (threadIdx.x == 0) s_guest = atomicAdd(next_item + 1 + smid(), 1u);
+    if (threadIdx.x == 0) s_guest = atomicAdd(next_item + 1 + (smid() & 511u), 1u);  // (the host zeroes 512 counters)
     __syncthreads();
     if (s_guest >= (unsigned int)guests) return;
     guest = true;
