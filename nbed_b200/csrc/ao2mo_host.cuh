@@ -55,12 +55,14 @@ static void ao2mo_device(nbd_ctx* c, int m, const double* ca, const double* cb) 
         if (naux == 0) {
           NBD_CUDA(cudaMemsetAsync(eri, 0, sizeof(double) * nblk * m4, c->stream));
         } else {
-          gemm_tn(c, (int)m2, (int)m2, naux, L, m2, L, m2, eri, m2);
+          // same-spin blocks are symmetric under (pq) <-> (rs): lower tiles + mirror (half the flops of two of the three)
+          gemm_tn(c, (int)m2, (int)m2, naux, L, m2, L, m2, eri, m2, 1.0, 0.0, 1, 0, 0, 0, /*lower=*/1);
           if (!restricted) {
             double* Lb = L + (long)naux * m2;
-            gemm_tn(c, (int)m2, (int)m2, naux, Lb, m2, Lb, m2, eri + m4, m2);
+            gemm_tn(c, (int)m2, (int)m2, naux, Lb, m2, Lb, m2, eri + m4, m2, 1.0, 0.0, 1, 0, 0, 0, /*lower=*/1);
             gemm_tn(c, (int)m2, (int)m2, naux, L, m2, Lb, m2, eri + 2 * m4, m2);
           }
+          symmetrize_lower(c, eri, (int)m2, restricted ? 1 : 2);
         }
       }
       all_reduce(c, eri, (size_t)nblk * m4);

@@ -289,6 +289,17 @@ inline cudaError_t launch_gemm(cudaStream_t st, GemmArgs g, int variant, long* l
     if (!a_mc && b_nc) return launch_gemm_cfg<BM, BN, WM, WN, false, true>(st, g); \
     return launch_gemm_cfg<BM, BN, WM, WN, false, false>(st, g);                   \
   } while (0)
+  // Narrow outputs (the second ao2mo half-transform L[(P,p)][q] = X C: N = m active orbitals, M = naux * m rows): a
+  // 64-column tile would spend 64 / N of the DMMAs on padding (37 % at m = 40), so the column extent of the tile is
+  // N rounded up to 8 - one warp per 16 rows, NI = BN / 8 accumulator columns.
+  if (force_tile == 0 && !a_mc && !b_nc && g.N > 16 && g.N <= 56 && g.M >= 64 * (long)sm_count) {
+    const int bn8 = (g.N + 7) / 8 * 8;
+    if (bn8 == 24) return launch_gemm_cfg<64, 24, 16, 24, false, false>(st, g);
+    if (bn8 == 32) return launch_gemm_cfg<64, 32, 16, 32, false, false>(st, g);
+    if (bn8 == 40) return launch_gemm_cfg<64, 40, 16, 40, false, false>(st, g);
+    if (bn8 == 48) return launch_gemm_cfg<64, 48, 16, 48, false, false>(st, g);
+    if (bn8 == 56) return launch_gemm_cfg<64, 56, 16, 56, false, false>(st, g);
+  }
   if (tile == 32) NBD_GEMM_DISPATCH(32, 32, 16, 16);
   if (tile == 64) NBD_GEMM_DISPATCH(64, 64, 32, 32);
   NBD_GEMM_DISPATCH(128, 128, 64, 32);
