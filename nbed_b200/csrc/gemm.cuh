@@ -266,6 +266,9 @@ inline cudaError_t launch_gemm(cudaStream_t st, GemmArgs g, int variant, long* l
   int tile = 128;
   if (ctas(128) < 3L * sm_count) tile = 64;
   if (tile == 64 && ctas(64) < (long)sm_count / 2 && g.M <= 256 && g.N <= 256) tile = 32;
+  // a thin output (M or N <= 32: the back-transform C = V^T X of the tracked 16 / 32 orbitals, the mu path's gradient
+  // blocks) on 64-tiles is 50-90 % padding on less than one wave of CTAs: 32-tiles halve the padding and double the CTAs
+  if (tile == 64 && ctas(64) < (long)sm_count && (g.M <= 32 || g.N <= 32)) tile = 32;
   if (force_tile == 32 || force_tile == 64 || force_tile == 128) tile = force_tile;
   if (variant == 1 || g.K <= 0) {
     dim3 b(32, 8), grid((g.N + 31) / 32, (g.M + 7) / 8, g.batch);
