@@ -37,7 +37,8 @@ static void scf_build_fock(nbd_ctx* c, int Ntot, const std::vector<KGroup>& grou
   jk_device(c, c->d_orb.p, c->d_wt.p, Ntot, 1, jbegin, buf, ns, groups, buf + nn);
   // UHF: J - K_s; RHF: J - K / 2; UKS: J - hyb K_s; RKS: J - hyb K / 2   (pyscf/dft/{uks,rks}.py:get_veff)
   const double kscale = (ks ? c->xc.hyb : 1.0) * (ns == 2 ? 1.0 : 0.5);
-  if (c->world > 1 && c->comm && c->packed_allreduce && !ks && n >= 256) {
+  // (option packed_allreduce = 2 takes this route on a single rank as well, where the all-reduce is a no-op: test hook)
+  if (((c->world > 1 && c->comm && c->packed_allreduce) || c->packed_allreduce == 2) && !ks && n >= 256) {
     // symmetric partial sums: the ranks exchange the lower triangles only (half the all-reduce bytes), and the Fock
     // assembly reads the packed sums directly.  (Kohn-Sham objects keep the square buffers: their traces read J and K.)
     const long npack = (long)n * (n + 1) / 2;

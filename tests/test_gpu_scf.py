@@ -485,3 +485,23 @@ def test_huzinaga_rhf_subspace_path_with_the_single_shot_block_product(ctx):
     for k, t in enumerate(tr[: info["cycles"]]):
         assert abs(info["trace"][k, 0] - float(t["energy"])) < E_TOL, k
     assert np.abs(d1 - d0).max() < 1e-8 and np.abs(h1 - h0).max() < 1e-7 and np.abs(e1 - e0).max() < 1e-8
+
+
+def test_packed_lower_fock_assembly_matches_the_square_route(ctx):
+    """The multi-GPU SCF loop all-reduces the packed lower triangles of [J | K_a | K_b] and assembles the Fock matrix
+    from the packed sums (scf_host.cuh: scf_build_fock).  Option packed_allreduce = 2 takes that route on one rank (the
+    all-reduce is a no-op there): the iterates must be bit-identical to the square route's."""
+    n, naux, nocc, n_env = 300, 20, 5, 8
+    p = syn.make_problem(n=n, naux=naux, nocc=nocc, n_env=n_env, seed=6, scale=3.0 / np.sqrt(n * naux))
+    ctx.load_cderi(p.cderi())
+    runs = {}
+    try:
+        for mode in (1, 2):
+            ctx.set_option("packed_allreduce", mode)
+            ctx.scf_setup(p.nelec, p.ovlp, p.hcore, p.v_emb, p.dm_enviro, NBD_HUZINAGA)
+            runs[mode] = ctx.huzinaga_scf(12, 1e-9, 1e-7, True)
+    finally:
+        ctx.set_option("packed_allreduce", 1)
+    a, b = runs[1], runs[2]
+    assert a[4]["cycles"] == b[4]["cycles"] and np.array_equal(a[4]["trace"], b[4]["trace"])
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
